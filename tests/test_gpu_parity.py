@@ -1,0 +1,143 @@
+"""GPU: the CUDA path (through the C ABI) against the committed reference outputs and the oracle.
+
+Tolerance: BASELINE.json's north_star asks for |ddG - reference| <= 1e-4 in fp32."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import CASES, load_case
+from thermompnn_b200.datasets import ALPHABET, Mutation
+from thermompnn_b200.featurize import featurize_batch
+from thermompnn_b200.ssm import get_ssm_mutations, to_mutation_objects
+from thermompnn_b200.synth import synth, synth_multichain
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _sets_equal(a, b):
+    return all(set(x[x >= 0].tolist()) == set(y.tolist()) for x, y in zip(a, b))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_ddg_matches_reference(name, gpu_model):
+    d, pdb = load_case(name)
+    ddg = gpu_model.ssm_tables([pdb])[0]
+    ref = d["ddG"]
+    ok = ~np.isnan(ref)
+    assert np.array_equal(np.isnan(ddg), ~ok)
+    err = np.abs(ddg - ref)[ok].max()
+    print(f"{name}: max |ddG_gpu - ddG_ref| = {err:.2e}")
+    assert err <= TOL
+    seq = pdb["seq"]
+    for i, a in enumerate(seq):
+        if a != "-" and a != "X":
+            assert ddg[i, ALPHABET.index(a)] == 0.0
+
+
+@pytest.mark.parametrize("name", ["2OCJ_A", "synth40", "synth120_gaps", "synth_multichain"])
+def test_layerwise(name, gpu_model):
+    d, pdb = load_case(name)
+    eng = gpu_model._get_engine()
+    p = featurize_batch([pdb])
+    L = p.n_residues
+    K = min(48, L)
+    valid = p.mask.astype(bool)
+    try:
+        eng.set_debug_stop(2)
+        eng.run(p.offsets, p.X, p.S, p.residue_idx, p.chain_enc, p.mask)
+        E_idx = eng.fetch("E_idx")
+        assert (E_idx[:, K:] == -1).all() and (E_idx[:, :K] >= 0).all()
+        # neighbour SETS of valid residues must equal the reference's (order is irrelevant downstream)
+        assert _sets_equal(E_idx[valid], d["E_idx"][valid])
+        assert (E_idx[valid][:, 0] == np.arange(L)[valid]).all()          # self first
+        # h_E after W_e, compared slot-by-slot where the order agrees
+        hE = eng.fetch("h_E")[:6, :K]
+        same = E_idx[:6, :K] == d["E_idx"][:6]
+        assert same.mean() > 0.9
+        assert np.abs(hE - d["h_E0_head"])[same].max() <= 2e-5
+        for l in range(3):
+            eng.set_debug_stop(3 + l)
+            eng.run(p.offsets, p.X, p.S, p.residue_idx, p.chain_enc, p.mask)
+            assert np.abs(eng.fetch("h_V") - d[f"enc{l}_h_V"]).max() <= 5e-5
+            hE = eng.fetch("h_E")[:6, :K]
+            assert np.abs(hE - d[f"enc{l}_h_E_head"])[same].max() <= 1e-4
+        for l in range(3):
+            eng.set_debug_stop(6 + l)
+            eng.run(p.offsets, p.X, p.S, p.residue_idx, p.chain_enc, p.mask)
+            assert np.abs(eng.fetch("h_V") - d[f"dec{l}_h_V"]).max() <= 5e-5
+    finally:
+        eng.set_debug_stop(0)
+
+
+def test_forward_contract(gpu_model):
+    """Same call the reference's scripts make (custom_inference.py:92-97)."""
+    d, pdb = load_case("2OCJ_A")
+    muts = to_mutation_objects(get_ssm_mutations(pdb), pdb["name"])
+    muts.insert(5, None)
+    with torch.no_grad():
+        pred, extra = gpu_model([pdb], muts)
+    assert extra is None and len(pred) == len(muts) and pred[5] is None
+    assert pred[0]["ddG"].shape == (1,) and pred[0]["ddG"].is_cuda and pred[0]["ddG"].dtype == torch.float32
+    got = np.asarray([p["ddG"].cpu().item() for p in pred if p is not None]).reshape(194, 20)
+    assert np.abs(got - d["ddG"]).max() <= TOL
+    with pytest.raises(ValueError):
+        gpu_model([pdb], [Mutation(0, "A", "B")])          # 'B' not in ALPHABET, as upstream
+    with pytest.raises(IndexError):
+        gpu_model([pdb], [Mutation(194, "A", "C")])
+
+
+def test_ragged_batch_equals_single_runs(gpu_model):
+    """A batch is defined as 'identical to running each protein alone' -- bit for bit."""
+    pdbs = [synth(40, 7), load_case("2OCJ_A")[1], synth(120, 11, gaps=[0, 17, 18, 19, 64, 119]),
+            synth_multichain([60, 50], 5), synth(49, 3), synth(7, 1), synth(1, 2), synth(301, 4)]
+    batch = gpu_model.head_tables(pdbs)
+    for pdb, Tb in zip(pdbs, batch):
+        T1 = gpu_model.head_tables([pdb])[0]
+        assert np.array_equal(Tb, T1), pdb["name"]
+    rev = gpu_model.head_tables(pdbs[::-1])[::-1]
+    for a, b in zip(batch, rev):
+        assert np.array_equal(a, b)
+
+
+def test_against_oracle_on_fresh_inputs(gpu_model, oracle_weights):
+    """Inputs with no committed fixture: the oracle is the checker (edge cases: tiny, K=L, gaps, two chains)."""
+    from oracle import thermompnn_oracle as O
+    pdbs = [synth(2, 5), synth(13, 6), synth(48, 8), synth(77, 9, gaps=[10, 11, 40]), synth_multichain([30, 31], 12),
+            synth(200, 13)]
+    for pdb, ddg in zip(pdbs, gpu_model.ssm_tables(pdbs)):
+        _, ref, _ = O.ssm_table(oracle_weights, pdb)
+        ok = ~np.isnan(ddg)
+        err = np.abs(ddg - ref.numpy())[ok].max()
+        print(pdb["name"], f"{err:.2e}")
+        assert err <= TOL
+
+
+def test_full_size_properties(gpu_model):
+    """At BASELINE sizes the oracle is too slow to be the checker; use size-independent properties:
+    finiteness, wt->wt == 0, invariance to a rigid motion of the whole structure (k-NN + distances only)."""
+    pdb = synth(2000, 2000)
+    ddg = gpu_model.ssm_tables([pdb])[0]
+    assert np.isfinite(ddg).all()
+    wt = np.asarray([ALPHABET.index(a) for a in pdb["seq"]])
+    assert (ddg[np.arange(2000), wt] == 0).all()
+    moved = dict(pdb)
+    co = {k: (np.asarray(v) + np.array([10.0, -20.0, 5.0])).round(3).tolist() for k, v in pdb["coords_chain_A"].items()}
+    moved["coords_chain_A"] = co
+    ddg2 = gpu_model.ssm_tables([moved])[0]
+    assert np.abs(ddg - ddg2).max() <= 2e-4
+
+
+def test_error_codes(gpu_model):
+    from thermompnn_b200 import engine
+    eng = gpu_model._get_engine()
+    p = featurize_batch([synth(10, 1)])
+    bad = p.S.copy(); bad[3] = 21
+    with pytest.raises(engine.EngineError, match="outside 0..20"):
+        eng.run(p.offsets, p.X, bad, p.residue_idx, p.chain_enc, p.mask)
+    with pytest.raises(engine.EngineError, match="empty protein|offsets"):
+        eng.run(np.asarray([0, 5, 5, 10], dtype=np.int32), p.X, p.S, p.residue_idx, p.chain_enc, p.mask)
+    fresh = engine.Engine(0)
+    with pytest.raises(engine.EngineError, match="weights not loaded"):
+        fresh.run(p.offsets, p.X, p.S, p.residue_idx, p.chain_enc, p.mask)
+    fresh.close()

@@ -1,0 +1,643 @@
+// thermompnn_b200 engine: the C ABI declared in include/thermompnn_b200.h.
+//
+// Owns the device state of one GPU: the prepared weight block, the per-batch
+// activation buffers (sized for the largest batch seen), a pinned staging buffer
+// for host inputs and one CUDA stream.  No CPU fallback exists: every entry
+// point that needs the GPU fails with TMPNN_E_CUDA when there is none.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/thermompnn_b200.h"
+#include "kernels.h"
+#include "weights.h"
+
+using namespace tmpnn;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct ProfEntry {
+    std::string name;
+    double total_ms = 0.0;
+    int64_t launches = 0;
+};
+
+struct PendingEvent {
+    int entry;
+    cudaEvent_t a, b;
+};
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 4;
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct tmpnn_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    std::vector<RawTensor> raw;
+    DevLayout lay{};
+    float* d_weights = nullptr;
+    bool have_weights = false;
+
+    // inputs (device mirror of the staging buffer)
+    DevBuf<unsigned char> d_in;
+    unsigned char* h_stage = nullptr;
+    size_t h_stage_cap = 0;
+    // per-node
+    DevBuf<int> pstart, pend;
+    DevBuf<float> atoms, maskf, hV, dec_prev, dec_last, Ssum, cnt, P, Q, P2, Q2, table;
+    // per-edge
+    DevBuf<int> E_idx;
+    DevBuf<float> D_nb, hE;
+
+    int last_N = 0;
+    float* last_table = nullptr;
+    int debug_stop = 0;
+
+    bool profiling = false;
+    std::vector<ProfEntry> prof;
+    std::vector<PendingEvent> pending;
+    std::vector<cudaEvent_t> event_pool;
+    int64_t launches = 0;
+};
+
+namespace {
+
+int fail(tmpnn_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(ctx, TMPNN_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));    \
+    } while (0)
+
+// ---------------- weight preparation (host) ---------------------------------
+struct Prep {
+    const float* raw;
+    const std::vector<RawTensor>& table;
+    std::vector<float> dev;
+    const float* find(const std::string& n, int* rows = nullptr, int* cols = nullptr) const {
+        for (auto& t : table)
+            if (t.name == n) {
+                if (rows) *rows = t.rows;
+                if (cols) *cols = t.cols;
+                return raw + t.offset;
+            }
+        return nullptr;
+    }
+    int64_t alloc(int64_t n) {
+        int64_t off = (int64_t)dev.size();
+        int64_t padded = (n + 31) / 32 * 32;   // keep every block 128-byte aligned
+        dev.resize(dev.size() + padded, 0.f);
+        return off;
+    }
+    // KN[k][n] = W[n][col0 + k] for a row-major nn.Linear weight W[out][in]
+    void put_kn(int64_t off, const std::string& name, int col0, int ncols) {
+        int out, in;
+        const float* W = find(name, &out, &in);
+        for (int k = 0; k < ncols; ++k)
+            for (int n = 0; n < out; ++n) dev[off + (int64_t)k * out + n] = W[(int64_t)n * in + col0 + k];
+    }
+    int64_t kn(const std::string& name, int col0 = 0, int ncols = -1) {
+        int out, in;
+        find(name, &out, &in);
+        if (ncols < 0) ncols = in;
+        int64_t off = alloc((int64_t)ncols * out);
+        put_kn(off, name, col0, ncols);
+        return off;
+    }
+    int64_t vec(const std::string& name) {
+        int r, c;
+        const float* v = find(name, &r, &c);
+        int64_t off = alloc((int64_t)r * c);
+        std::copy(v, v + (int64_t)r * c, dev.begin() + off);
+        return off;
+    }
+    LayerNormW ln(const std::string& p) { return {vec(p + ".weight"), vec(p + ".bias")}; }
+    NodeUpdW node_upd(const std::string& p) {
+        NodeUpdW w;
+        w.W3 = kn(p + "W3.weight");
+        w.b3 = vec(p + "W3.bias");
+        w.n1 = ln(p + "norm1");
+        w.n2 = ln(p + "norm2");
+        w.Win = kn(p + "dense.W_in.weight");
+        w.bin = vec(p + "dense.W_in.bias");
+        w.Wout = kn(p + "dense.W_out.weight");
+        w.bout = vec(p + "dense.W_out.bias");
+        return w;
+    }
+};
+
+DevLayout prepare_weights(Prep& P) {
+    DevLayout L{};
+    const std::string pm = "prot_mpnn.";
+    {   // positional table: Linear(one_hot(q)) = W[:, q] + b   (protein_mpnn_utils.py:906-907)
+        const float* W = P.find(pm + "features.embeddings.linear.weight");
+        const float* b = P.find(pm + "features.embeddings.linear.bias");
+        L.pos_table = P.alloc(66 * 16);
+        for (int q = 0; q < 66; ++q)
+            for (int t = 0; t < 16; ++t) P.dev[L.pos_table + q * 16 + t] = W[t * 66 + q] + b[t];
+    }
+    L.feat = P.alloc((int64_t)(EDGE_IN + HID) * HID);
+    P.put_kn(L.feat, pm + "features.edge_embedding.weight", 0, EDGE_IN);
+    P.put_kn(L.feat + (int64_t)EDGE_IN * HID, pm + "W_e.weight", 0, HID);
+    L.be = P.vec(pm + "W_e.bias");
+    L.ne = P.ln(pm + "features.norm_edges");
+    {   // torch.linspace(2., 22., 16) in fp32 (protein_mpnn_utils.py:1113-1114)
+        L.rbf_mu = P.alloc(16);
+        const float start = 2.0f, end = 22.0f;
+        const float step = (end - start) / 15.0f;
+        for (int i = 0; i < 16; ++i)
+            P.dev[L.rbf_mu + i] = (i < 8) ? start + step * (float)i : end - step * (float)(15 - i);
+    }
+    for (int l = 0; l < 3; ++l) {
+        const std::string p = pm + "encoder_layers." + std::to_string(l) + ".";
+        EncW& e = L.enc[l];
+        e.msg = P.alloc(2 * HID * HID);
+        P.put_kn(e.msg, p + "W1.weight", HID, HID);
+        P.put_kn(e.msg + HID * HID, p + "W2.weight", 0, HID);
+        e.b1 = P.vec(p + "W1.bias");
+        e.b2 = P.vec(p + "W2.bias");
+        e.W1a = P.kn(p + "W1.weight", 0, HID);
+        e.W1c = P.kn(p + "W1.weight", 2 * HID, HID);
+        e.edge = P.alloc(3 * HID * HID);
+        P.put_kn(e.edge, p + "W11.weight", HID, HID);
+        P.put_kn(e.edge + HID * HID, p + "W12.weight", 0, HID);
+        P.put_kn(e.edge + 2 * HID * HID, p + "W13.weight", 0, HID);
+        e.b11 = P.vec(p + "W11.bias");
+        e.b12 = P.vec(p + "W12.bias");
+        e.b13 = P.vec(p + "W13.bias");
+        e.W11a = P.kn(p + "W11.weight", 0, HID);
+        e.W11c = P.kn(p + "W11.weight", 2 * HID, HID);
+        e.n3 = P.ln(p + "norm3");
+        e.nu = P.node_upd(p);
+    }
+    const float* Ws = P.find(pm + "W_s.weight");
+    for (int l = 0; l < 3; ++l) {
+        const std::string p = pm + "decoder_layers." + std::to_string(l) + ".";
+        DecW& d = L.dec[l];
+        d.msg = P.alloc(2 * HID * HID);
+        P.put_kn(d.msg, p + "W1.weight", HID, HID);
+        P.put_kn(d.msg + HID * HID, p + "W2.weight", 0, HID);
+        d.b1 = P.vec(p + "W1.bias");
+        d.b2 = P.vec(p + "W2.bias");
+        d.W1a = P.kn(p + "W1.weight", 0, HID);
+        d.W1d = P.kn(p + "W1.weight", 3 * HID, HID);
+        // h_S[j] term: W1[:, 256:384] . W_s[S_j]  -> one row per letter
+        const float* W1 = P.find(p + "W1.weight");
+        d.Tseq = P.alloc(21 * HID);
+        for (int a = 0; a < 21; ++a)
+            for (int n = 0; n < HID; ++n) {
+                double s = 0.0;
+                for (int k = 0; k < HID; ++k) s += (double)Ws[a * HID + k] * (double)W1[(int64_t)n * 4 * HID + 2 * HID + k];
+                P.dev[d.Tseq + a * HID + n] = (float)s;
+            }
+        d.nu = P.node_upd(p);
+    }
+    L.Ws = P.vec(pm + "W_s.weight");
+    L.la = P.kn("light_attention.feature_convolution.weight_center");
+    L.la_b = P.vec("light_attention.feature_convolution.bias");
+    L.m1 = P.kn("both_out.1.weight"); L.m1_b = P.vec("both_out.1.bias");
+    L.m2 = P.kn("both_out.3.weight"); L.m2_b = P.vec("both_out.3.bias");
+    L.m3 = P.kn("both_out.5.weight"); L.m3_b = P.vec("both_out.5.bias");
+    L.ddg = P.alloc(2);
+    P.dev[L.ddg] = *P.find("ddg_out.weight");
+    P.dev[L.ddg + 1] = *P.find("ddg_out.bias");
+    L.zeros = P.alloc(HID);
+    L.total = (int64_t)P.dev.size();
+    return L;
+}
+
+// ---------------- profiling helpers ------------------------------------------
+int prof_entry(tmpnn_ctx* c, const char* name) {
+    for (size_t i = 0; i < c->prof.size(); ++i)
+        if (c->prof[i].name == name) return (int)i;
+    c->prof.push_back({name, 0.0, 0});
+    return (int)c->prof.size() - 1;
+}
+
+cudaEvent_t get_event(tmpnn_ctx* c) {
+    if (!c->event_pool.empty()) {
+        cudaEvent_t e = c->event_pool.back();
+        c->event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct LaunchScope {   // brackets one kernel launch with events when profiling
+    tmpnn_ctx* c;
+    cudaStream_t st;
+    PendingEvent pe{};
+    bool on;
+    LaunchScope(tmpnn_ctx* c_, cudaStream_t st_, const char* name) : c(c_), st(st_), on(c_->profiling) {
+        c->launches++;
+        if (on) {
+            pe.entry = prof_entry(c, name);
+            pe.a = get_event(c);
+            pe.b = get_event(c);
+            cudaEventRecord(pe.a, st);
+        }
+    }
+    ~LaunchScope() {
+        if (on) {
+            cudaEventRecord(pe.b, st);
+            c->pending.push_back(pe);
+        }
+    }
+};
+
+void drain_profile(tmpnn_ctx* c) {
+    for (auto& pe : c->pending) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(pe.b) == cudaSuccess && cudaEventElapsedTime(&ms, pe.a, pe.b) == cudaSuccess) {
+            c->prof[pe.entry].total_ms += ms;
+            c->prof[pe.entry].launches += 1;
+        }
+        c->event_pool.push_back(pe.a);
+        c->event_pool.push_back(pe.b);
+    }
+    c->pending.clear();
+}
+
+size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+// Residues per tile: minimise (waves over the SMs) x (tile size), preferring big tiles when the grid is deep.
+int choose_npt(int N, int sms) {
+    int best = 4;
+    double best_cost = 1e30;
+    for (int npt = 1; npt <= 4; ++npt) {
+        int tiles = (N + npt - 1) / npt;
+        int waves = (tiles + sms - 1) / sms;
+        double cost = (double)waves * (npt + 0.35);
+        if (cost < best_cost - 1e-9 || (std::fabs(cost - best_cost) < 1e-9 && npt > best)) {
+            best_cost = cost;
+            best = npt;
+        }
+    }
+    if (N >= 16 * sms) best = 4;
+    return best;
+}
+
+}  // namespace
+
+// =============================================================================
+// C ABI
+// =============================================================================
+extern "C" {
+
+int tmpnn_abi_version(void) { return TMPNN_ABI_VERSION; }
+
+static const std::vector<RawTensor>& raw_table() {
+    static const std::vector<RawTensor> t = build_raw_table();
+    return t;
+}
+
+int tmpnn_weight_count(void) { return (int)raw_table().size(); }
+
+int tmpnn_weight_info(int index, const char** name, int64_t* offset, int32_t* rows, int32_t* cols) {
+    const auto& t = raw_table();
+    if (index < 0 || index >= (int)t.size()) return TMPNN_E_INVALID;
+    if (name) *name = t[index].name.c_str();
+    if (offset) *offset = t[index].offset;
+    if (rows) *rows = t[index].rows;
+    if (cols) *cols = t[index].cols;
+    return TMPNN_OK;
+}
+
+int64_t tmpnn_weight_blob_floats(void) {
+    const auto& t = raw_table();
+    return t.back().offset + (int64_t)t.back().rows * t.back().cols;
+}
+
+int tmpnn_create(int device, tmpnn_ctx** out) {
+    if (!out) {
+        g_create_error = "tmpnn_create: out is NULL";
+        return TMPNN_E_INVALID;
+    }
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("tmpnn_create: no CUDA device (") + cudaGetErrorString(e) +
+                         "); thermompnn_b200 has no CPU path";
+        return TMPNN_E_CUDA;
+    }
+    if (device < 0 || device >= ndev) {
+        g_create_error = "tmpnn_create: device index out of range";
+        return TMPNN_E_INVALID;
+    }
+    tmpnn_ctx* ctx = new tmpnn_ctx();
+    ctx->device = device;
+    ctx->raw = raw_table();
+    auto bail = [&](const std::string& m) {
+        g_create_error = m;
+        delete ctx;
+        return TMPNN_E_CUDA;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+        return bail(std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
+    if (prop.major != 10)
+        return bail("tmpnn_create: device is sm_" + std::to_string(prop.major * 10 + prop.minor) +
+                    ", this library is built for sm_100a (B200) only");
+    ctx->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return bail(std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+    if ((e = kernels_init()) != cudaSuccess) return bail(std::string("kernels_init: ") + cudaGetErrorString(e));
+    *out = ctx;
+    return TMPNN_OK;
+}
+
+void tmpnn_destroy(tmpnn_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    drain_profile(ctx);
+    for (auto e : ctx->event_pool) cudaEventDestroy(e);
+    if (ctx->d_weights) cudaFree(ctx->d_weights);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    ctx->d_in.release();
+    ctx->pstart.release(); ctx->pend.release();
+    ctx->atoms.release(); ctx->maskf.release(); ctx->hV.release(); ctx->dec_prev.release(); ctx->dec_last.release();
+    ctx->Ssum.release(); ctx->cnt.release(); ctx->P.release(); ctx->Q.release(); ctx->P2.release(); ctx->Q2.release();
+    ctx->table.release(); ctx->E_idx.release(); ctx->D_nb.release(); ctx->hE.release();
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* tmpnn_last_error(const tmpnn_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int tmpnn_load_weights(tmpnn_ctx* ctx, const float* host_blob, int64_t n_floats) {
+    if (!ctx) return TMPNN_E_INVALID;
+    if (!host_blob) return fail(ctx, TMPNN_E_INVALID, "tmpnn_load_weights: blob is NULL");
+    if (n_floats != tmpnn_weight_blob_floats())
+        return fail(ctx, TMPNN_E_RANGE, "tmpnn_load_weights: blob has " + std::to_string(n_floats) + " floats, expected " +
+                                            std::to_string(tmpnn_weight_blob_floats()));
+    for (int64_t i = 0; i < n_floats; ++i)
+        if (!std::isfinite(host_blob[i])) return fail(ctx, TMPNN_E_INVALID, "tmpnn_load_weights: non-finite weight");
+    Prep P{host_blob, ctx->raw, {}};
+    ctx->lay = prepare_weights(P);
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->d_weights) cudaFree(ctx->d_weights);
+    ctx->d_weights = nullptr;
+    ctx->have_weights = false;
+    CU(cudaMalloc(&ctx->d_weights, P.dev.size() * sizeof(float)));
+    CU(cudaMemcpyAsync(ctx->d_weights, P.dev.data(), P.dev.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->have_weights = true;
+    return TMPNN_OK;
+}
+
+int tmpnn_run_batch(tmpnn_ctx* ctx, int32_t B, const int32_t* offsets, const float* X, const int32_t* S,
+                    const int32_t* residue_idx, const int32_t* chain_enc, const uint8_t* mask, float* out_table,
+                    uint32_t flags, void* stream_) {
+    if (!ctx) return TMPNN_E_INVALID;
+    if (!ctx->have_weights) return fail(ctx, TMPNN_E_NOWEIGHTS, "tmpnn_run_batch: weights not loaded");
+    if (B <= 0 || !offsets || !X || !S || !residue_idx || !chain_enc || !mask || !out_table)
+        return fail(ctx, TMPNN_E_INVALID, "tmpnn_run_batch: NULL pointer or B <= 0");
+    if (offsets[0] != 0) return fail(ctx, TMPNN_E_INVALID, "tmpnn_run_batch: offsets[0] must be 0");
+    int lmax = 0;
+    for (int b = 0; b < B; ++b) {
+        int len = offsets[b + 1] - offsets[b];
+        if (len <= 0) return fail(ctx, TMPNN_E_INVALID, "tmpnn_run_batch: empty protein or unsorted offsets at " + std::to_string(b));
+        lmax = std::max(lmax, len);
+    }
+    if (lmax > knn_max_len())
+        return fail(ctx, TMPNN_E_RANGE, "tmpnn_run_batch: protein longer than " + std::to_string(knn_max_len()) + " residues");
+    const int N = offsets[B];
+    const bool in_dev = flags & TMPNN_IN_DEVICE, out_dev = flags & TMPNN_OUT_DEVICE;
+    if (!in_dev) {
+        for (int i = 0; i < N; ++i)
+            if (S[i] < 0 || S[i] > 20) return fail(ctx, TMPNN_E_RANGE, "tmpnn_run_batch: S[" + std::to_string(i) + "] outside 0..20");
+    }
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream_ ? (cudaStream_t)stream_ : ctx->stream;
+
+    // ---- inputs -------------------------------------------------------------
+    const size_t o_off = 0;
+    const size_t o_X = align16(o_off + (size_t)(B + 1) * 4);
+    const size_t o_S = align16(o_X + (size_t)N * 48);
+    const size_t o_r = align16(o_S + (size_t)N * 4);
+    const size_t o_c = align16(o_r + (size_t)N * 4);
+    const size_t o_m = align16(o_c + (size_t)N * 4);
+    const size_t in_bytes = align16(o_m + (size_t)N);
+    const size_t used = in_dev ? align16((size_t)(B + 1) * 4) : in_bytes;
+    CU(ctx->d_in.reserve(used));
+    if (ctx->h_stage_cap < used) {
+        if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+        ctx->h_stage = nullptr;
+        ctx->h_stage_cap = 0;
+        CU(cudaMallocHost(&ctx->h_stage, used + used / 4));
+        ctx->h_stage_cap = used + used / 4;
+    }
+    std::memcpy(ctx->h_stage + o_off, offsets, (size_t)(B + 1) * 4);
+    const int* d_off = reinterpret_cast<const int*>(ctx->d_in.p + o_off);
+    const float* d_X = X;
+    const int *d_S = S, *d_r = residue_idx, *d_c = chain_enc;
+    const uint8_t* d_m = mask;
+    if (!in_dev) {
+        std::memcpy(ctx->h_stage + o_X, X, (size_t)N * 48);
+        std::memcpy(ctx->h_stage + o_S, S, (size_t)N * 4);
+        std::memcpy(ctx->h_stage + o_r, residue_idx, (size_t)N * 4);
+        std::memcpy(ctx->h_stage + o_c, chain_enc, (size_t)N * 4);
+        std::memcpy(ctx->h_stage + o_m, mask, (size_t)N);
+        d_X = reinterpret_cast<const float*>(ctx->d_in.p + o_X);
+        d_S = reinterpret_cast<const int*>(ctx->d_in.p + o_S);
+        d_r = reinterpret_cast<const int*>(ctx->d_in.p + o_r);
+        d_c = reinterpret_cast<const int*>(ctx->d_in.p + o_c);
+        d_m = ctx->d_in.p + o_m;
+    }
+    CU(cudaMemcpyAsync(ctx->d_in.p, ctx->h_stage, used, cudaMemcpyHostToDevice, st));
+
+    // ---- buffers --------------------------------------------------------------
+    const size_t n = (size_t)N, ne = n * KNB;
+    CU(ctx->pstart.reserve(n)); CU(ctx->pend.reserve(n));
+    CU(ctx->atoms.reserve(n * 16)); CU(ctx->maskf.reserve(n));
+    CU(ctx->hV.reserve(n * HID)); CU(ctx->dec_prev.reserve(n * HID)); CU(ctx->dec_last.reserve(n * HID));
+    CU(ctx->Ssum.reserve(n * HID)); CU(ctx->cnt.reserve(n));
+    CU(ctx->P.reserve(n * HID)); CU(ctx->Q.reserve(n * HID)); CU(ctx->P2.reserve(n * HID)); CU(ctx->Q2.reserve(n * HID));
+    CU(ctx->E_idx.reserve(ne)); CU(ctx->D_nb.reserve(ne)); CU(ctx->hE.reserve(ne * HID));
+    float* d_table = out_table;
+    if (!out_dev) {
+        CU(ctx->table.reserve(n * 21));
+        d_table = ctx->table.p;
+    }
+    ctx->last_N = N;
+    ctx->last_table = d_table;
+
+    const float* W = ctx->d_weights;
+    const DevLayout& L = ctx->lay;
+    const int npt = choose_npt(N, ctx->sm_count);
+    const int stop = ctx->debug_stop;
+    bool done = false;
+    auto stage_done = [&](int s) { if (stop == s) done = true; return done; };
+
+    // ---- pipeline ---------------------------------------------------------------
+    { LaunchScope ls(ctx, st, "prep_nodes");
+      launch_prep_nodes(d_off, B, d_X, d_m, N, ctx->pstart.p, ctx->pend.p, ctx->atoms.p, ctx->maskf.p, st); }
+    { LaunchScope ls(ctx, st, "knn");
+      launch_knn(ctx->atoms.p, ctx->maskf.p, ctx->pstart.p, ctx->pend.p, N, lmax, ctx->E_idx.p, ctx->D_nb.p, st); }
+    if (!stage_done(1)) {
+        { LaunchScope ls(ctx, st, "edge_feat");
+          launch_edge_feat(npt, ctx->atoms.p, ctx->E_idx.p, ctx->D_nb.p, d_r, d_c, W + L.pos_table, W + L.rbf_mu,
+                           W + L.feat, W + L.ne.g, W + L.ne.b, W + L.be, ctx->hE.p, N, st); }
+        CU(cudaMemsetAsync(ctx->hV.p, 0, n * HID * sizeof(float), st));
+    }
+    if (!done && !stage_done(2)) {
+        for (int l = 0; l < 3 && !done; ++l) {
+            const EncW& e = L.enc[l];
+            { LaunchScope ls(ctx, st, "enc_msg");
+              if (l == 0)   // h_V = 0: P_i = b1, Q_j = 0
+                  launch_msg(npt, false, ctx->hE.p, ctx->E_idx.p, W + e.b1, 0, W + L.zeros, 0, ctx->maskf.p, W + e.msg,
+                             W + e.b2, ctx->Ssum.p, ctx->cnt.p, N, st);
+              else
+                  launch_msg(npt, false, ctx->hE.p, ctx->E_idx.p, ctx->P.p, HID, ctx->Q.p, HID, ctx->maskf.p, W + e.msg,
+                             W + e.b2, ctx->Ssum.p, ctx->cnt.p, N, st); }
+            NodeUpdArgs a{};
+            a.weights = W; a.w = e.nu; a.Ssum = ctx->Ssum.p; a.cnt = ctx->cnt.p; a.hV = ctx->hV.p; a.hV_copy = nullptr;
+            a.maskf = ctx->maskf.p; a.S = d_S; a.N = N;
+            a.proj[0] = {e.W11a, e.b11, -1, ctx->P2.p};     // edge update of this layer
+            a.proj[1] = {e.W11c, -1, -1, ctx->Q2.p};
+            if (l < 2) {
+                const EncW& nx = L.enc[l + 1];
+                a.proj[2] = {nx.W1a, nx.b1, -1, ctx->P.p};
+                a.proj[3] = {nx.W1c, -1, -1, ctx->Q.p};
+            } else {
+                const DecW& nx = L.dec[0];
+                a.proj[2] = {nx.W1a, nx.b1, -1, ctx->P.p};
+                a.proj[3] = {nx.W1d, -1, nx.Tseq, ctx->Q.p};
+            }
+            a.nproj = 4;
+            { LaunchScope ls(ctx, st, "node_update"); launch_node_update(a, st); }
+            { LaunchScope ls(ctx, st, "edge_upd");
+              launch_edge_upd(npt, ctx->hE.p, ctx->E_idx.p, ctx->P2.p, ctx->Q2.p, W + e.edge, W + e.b12, W + e.b13,
+                              W + e.n3.g, W + e.n3.b, N, st); }
+            stage_done(3 + l);
+        }
+    }
+    if (!done) {
+        for (int l = 0; l < 3 && !done; ++l) {
+            const DecW& d = L.dec[l];
+            { LaunchScope ls(ctx, st, "dec_msg");
+              launch_msg(npt, true, ctx->hE.p, ctx->E_idx.p, ctx->P.p, HID, ctx->Q.p, HID, ctx->maskf.p, W + d.msg,
+                         W + d.b2, ctx->Ssum.p, ctx->cnt.p, N, st); }
+            NodeUpdArgs a{};
+            a.weights = W; a.w = d.nu; a.Ssum = ctx->Ssum.p; a.cnt = ctx->cnt.p; a.hV = ctx->hV.p;
+            a.hV_copy = (l == 1) ? ctx->dec_prev.p : (l == 2 ? ctx->dec_last.p : nullptr);
+            a.maskf = ctx->maskf.p; a.S = d_S; a.N = N;
+            a.nproj = 0;
+            if (l < 2) {
+                const DecW& nx = L.dec[l + 1];
+                a.proj[0] = {nx.W1a, nx.b1, -1, ctx->P.p};
+                a.proj[1] = {nx.W1d, -1, nx.Tseq, ctx->Q.p};
+                a.nproj = 2;
+            }
+            { LaunchScope ls(ctx, st, "node_update"); launch_node_update(a, st); }
+            stage_done(6 + l);
+        }
+    }
+    if (!done) {
+        HeadArgs h{};
+        h.weights = W; h.Ws = L.Ws; h.la = L.la; h.la_b = L.la_b; h.m1 = L.m1; h.m1_b = L.m1_b; h.m2 = L.m2;
+        h.m2_b = L.m2_b; h.m3 = L.m3; h.m3_b = L.m3_b; h.ddg = L.ddg;
+        h.dec_last = ctx->dec_last.p; h.dec_prev = ctx->dec_prev.p; h.S = d_S; h.table = d_table; h.N = N;
+        { LaunchScope ls(ctx, st, "head"); launch_head(h, st); }
+        if (!out_dev) CU(cudaMemcpyAsync(out_table, d_table, n * 21 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaGetLastError());
+    if (!(flags & TMPNN_NO_SYNC) || !out_dev) {
+        CU(cudaStreamSynchronize(st));
+        if (ctx->profiling) drain_profile(ctx);
+    }
+    return TMPNN_OK;
+}
+
+int tmpnn_fetch(tmpnn_ctx* ctx, const char* name, void* host_dst, int64_t bytes) {
+    if (!ctx || !name || !host_dst) return TMPNN_E_INVALID;
+    const size_t n = (size_t)ctx->last_N;
+    if (n == 0) return fail(ctx, TMPNN_E_INVALID, "tmpnn_fetch: no batch has been run");
+    const void* src = nullptr;
+    size_t sz = 0;
+    const std::string s = name;
+    if (s == "E_idx") { src = ctx->E_idx.p; sz = n * KNB * 4; }
+    else if (s == "D_nb") { src = ctx->D_nb.p; sz = n * KNB * 4; }
+    else if (s == "h_E") { src = ctx->hE.p; sz = n * KNB * HID * 4; }
+    else if (s == "h_V") { src = ctx->hV.p; sz = n * HID * 4; }
+    else if (s == "dec1") { src = ctx->dec_prev.p; sz = n * HID * 4; }
+    else if (s == "dec2") { src = ctx->dec_last.p; sz = n * HID * 4; }
+    else if (s == "table") { src = ctx->last_table; sz = n * 21 * 4; }
+    else return fail(ctx, TMPNN_E_NOTFOUND, "tmpnn_fetch: unknown tensor '" + s + "'");
+    if ((size_t)bytes != sz)
+        return fail(ctx, TMPNN_E_RANGE, "tmpnn_fetch: '" + s + "' is " + std::to_string(sz) + " bytes, caller gave " + std::to_string(bytes));
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy(host_dst, src, sz, cudaMemcpyDeviceToHost));
+    return TMPNN_OK;
+}
+
+int tmpnn_set_debug_stop(tmpnn_ctx* ctx, int stage) {
+    if (!ctx || stage < 0 || stage > 8) return TMPNN_E_INVALID;
+    ctx->debug_stop = stage;
+    return TMPNN_OK;
+}
+
+int tmpnn_set_profiling(tmpnn_ctx* ctx, int enabled) {
+    if (!ctx) return TMPNN_E_INVALID;
+    ctx->profiling = enabled != 0;
+    return TMPNN_OK;
+}
+
+int tmpnn_profile_count(tmpnn_ctx* ctx) { return ctx ? (int)ctx->prof.size() : TMPNN_E_INVALID; }
+
+int tmpnn_profile_get(tmpnn_ctx* ctx, int index, const char** kernel_name, double* total_ms, int64_t* launches) {
+    if (!ctx || index < 0 || index >= (int)ctx->prof.size()) return TMPNN_E_INVALID;
+    if (kernel_name) *kernel_name = ctx->prof[index].name.c_str();
+    if (total_ms) *total_ms = ctx->prof[index].total_ms;
+    if (launches) *launches = ctx->prof[index].launches;
+    return TMPNN_OK;
+}
+
+int tmpnn_profile_reset(tmpnn_ctx* ctx) {
+    if (!ctx) return TMPNN_E_INVALID;
+    drain_profile(ctx);
+    ctx->prof.clear();
+    ctx->launches = 0;
+    return TMPNN_OK;
+}
+
+int64_t tmpnn_launch_count(const tmpnn_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,60 @@
+// Host-visible launch interface of kernels.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "weights.h"
+
+namespace tmpnn {
+
+struct ProjSpec {      // out[i] = h_V[i] . W (+ bias) (+ table[S_i])
+    int64_t W;         // KN [128][128], offset into the device weight block
+    int64_t bias;      // offset or -1
+    int64_t table;     // [21][128] offset or -1
+    float* out;        // [N][128]
+};
+
+struct NodeUpdArgs {
+    const float* weights;
+    NodeUpdW w;
+    const float* Ssum;   // [N][128] masked neighbour sum of the second GELU
+    const float* cnt;    // [N] sum of edge weights
+    float* hV;           // [N][128] in/out
+    float* hV_copy;      // optional second destination (decoder states kept for the head)
+    const float* maskf;  // [N]
+    const int* S;        // [N]
+    ProjSpec proj[4];
+    int nproj;
+    int N;
+};
+
+struct HeadArgs {
+    const float* weights;
+    int64_t Ws, la, la_b, m1, m1_b, m2, m2_b, m3, m3_b, ddg;
+    const float* dec_last;  // [N][128] output of the last decoder layer
+    const float* dec_prev;  // [N][128] output of the one before
+    const int* S;
+    float* table;           // [N][21]
+    int N;
+};
+
+cudaError_t kernels_init();
+int knn_max_len();
+
+void launch_prep_nodes(const int* offsets, int B, const float* X, const uint8_t* mask, int N, int* pstart, int* pend,
+                       float* atoms, float* maskf, cudaStream_t st);
+void launch_knn(const float* atoms, const float* maskf, const int* pstart, const int* pend, int N, int lmax,
+                int* E_idx, float* D_nb, cudaStream_t st);
+void launch_edge_feat(int npt, const float* atoms, const int* E_idx, const float* D_nb, const int* ridx,
+                      const int* cenc, const float* pos_table, const float* rbf_mu, const float* wstream,
+                      const float* ln_g, const float* ln_b, const float* b_e, float* hE, int N, cudaStream_t st);
+void launch_msg(int npt, bool dec, const float* hE, const int* E_idx, const float* P, int p_stride, const float* Q,
+                int q_stride, const float* maskf, const float* wstream, const float* b2, float* Ssum, float* cnt,
+                int N, cudaStream_t st);
+void launch_edge_upd(int npt, float* hE, const int* E_idx, const float* P, const float* Q, const float* wstream,
+                     const float* b12, const float* b13, const float* ln_g, const float* ln_b, int N,
+                     cudaStream_t st);
+void launch_node_update(const NodeUpdArgs& a, cudaStream_t st);
+void launch_head(const HeadArgs& a, cudaStream_t st);
+
+}  // namespace tmpnn

@@ -1,0 +1,134 @@
+// Weight contract and device layout.
+//
+// RAW: the reference checkpoint tensors (models/thermoMPNN_default.pt, names with the
+// Lightning "model." prefix stripped, see train_thermompnn.py:30-32 / transfer_model.py:42-73),
+// packed row-major into one host blob; tmpnn_weight_info() reports this table.
+//
+// DEV: what the kernels read.  nn.Linear weights [out,in] are transposed to [k=in][n=out]
+// rows ("KN"), W1/W11 are split into their h_V[i] / h_E / h_V[j] column blocks
+// (protein_mpnn_utils.py:819-822: h_EV = [h_V_i | h_E | h_V_j]), and the matrices one kernel
+// streams are stored back to back in the order it consumes them.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace tmpnn {
+
+constexpr int KNB = 48;     // neighbour slots per residue (checkpoint num_edges, transfer_model.py:26)
+constexpr int HID = 128;    // hidden width
+constexpr int NRBF = 16;
+constexpr int NPAIR = 25;
+constexpr int EDGE_IN = 416;  // 16 positional + 25*16 RBF (protein_mpnn_utils.py:1098)
+constexpr float LN_EPS = 1e-5f;
+constexpr float MSG_SCALE = 30.0f;  // EncLayer/DecLayer scale (protein_mpnn_utils.py:795,843)
+
+struct RawTensor {
+    std::string name;
+    int rows, cols;
+    int64_t offset;
+};
+
+inline std::vector<RawTensor> build_raw_table() {
+    std::vector<RawTensor> t;
+    int64_t off = 0;
+    auto add = [&](const std::string& n, int r, int c) {
+        t.push_back({n, r, c, off});
+        off += (int64_t)r * c;
+    };
+    const std::string pm = "prot_mpnn.";
+    add(pm + "features.embeddings.linear.weight", 16, 66);
+    add(pm + "features.embeddings.linear.bias", 1, 16);
+    add(pm + "features.edge_embedding.weight", 128, 416);
+    add(pm + "features.norm_edges.weight", 1, 128);
+    add(pm + "features.norm_edges.bias", 1, 128);
+    add(pm + "W_e.weight", 128, 128);
+    add(pm + "W_e.bias", 1, 128);
+    add(pm + "W_s.weight", 21, 128);
+    for (int l = 0; l < 3; ++l) {
+        std::string p = pm + "encoder_layers." + std::to_string(l) + ".";
+        for (const char* n : {"norm1", "norm2", "norm3"}) {
+            add(p + n + ".weight", 1, 128);
+            add(p + n + ".bias", 1, 128);
+        }
+        add(p + "W1.weight", 128, 384); add(p + "W1.bias", 1, 128);
+        add(p + "W2.weight", 128, 128); add(p + "W2.bias", 1, 128);
+        add(p + "W3.weight", 128, 128); add(p + "W3.bias", 1, 128);
+        add(p + "W11.weight", 128, 384); add(p + "W11.bias", 1, 128);
+        add(p + "W12.weight", 128, 128); add(p + "W12.bias", 1, 128);
+        add(p + "W13.weight", 128, 128); add(p + "W13.bias", 1, 128);
+        add(p + "dense.W_in.weight", 512, 128); add(p + "dense.W_in.bias", 1, 512);
+        add(p + "dense.W_out.weight", 128, 512); add(p + "dense.W_out.bias", 1, 128);
+    }
+    for (int l = 0; l < 3; ++l) {
+        std::string p = pm + "decoder_layers." + std::to_string(l) + ".";
+        for (const char* n : {"norm1", "norm2"}) {
+            add(p + n + ".weight", 1, 128);
+            add(p + n + ".bias", 1, 128);
+        }
+        add(p + "W1.weight", 128, 512); add(p + "W1.bias", 1, 128);
+        add(p + "W2.weight", 128, 128); add(p + "W2.bias", 1, 128);
+        add(p + "W3.weight", 128, 128); add(p + "W3.bias", 1, 128);
+        add(p + "dense.W_in.weight", 512, 128); add(p + "dense.W_in.bias", 1, 512);
+        add(p + "dense.W_out.weight", 128, 512); add(p + "dense.W_out.bias", 1, 128);
+    }
+    add(pm + "W_out.weight", 21, 128);
+    add(pm + "W_out.bias", 1, 21);
+    add("light_attention.feature_convolution.weight_center", 384, 384);
+    add("light_attention.feature_convolution.bias", 1, 384);
+    add("both_out.1.weight", 64, 384); add("both_out.1.bias", 1, 64);
+    add("both_out.3.weight", 32, 64);  add("both_out.3.bias", 1, 32);
+    add("both_out.5.weight", 21, 32);  add("both_out.5.bias", 1, 21);
+    add("ddg_out.weight", 1, 1);
+    add("ddg_out.bias", 1, 1);
+    return t;
+}
+
+// ---- device layout (offsets in floats into one allocation) ------------------
+struct LayerNormW { int64_t g, b; };
+
+struct NodeUpdW {           // what node_update needs for one Enc/Dec layer
+    int64_t W3, b3;         // KN [128][128]
+    LayerNormW n1, n2;
+    int64_t Win, bin;       // KN [128][512]
+    int64_t Wout, bout;     // KN [512][128]
+};
+
+struct EncW {
+    int64_t msg;            // [W1b | W2] KN, 8 chunks      (message kernel stream)
+    int64_t b1, b2;
+    int64_t W1a, W1c;       // KN: h_V[i] / h_V[j] blocks of W1
+    int64_t edge;           // [W11b | W12 | W13] KN, 12 chunks (edge-update stream)
+    int64_t b11, b12, b13;
+    int64_t W11a, W11c;
+    LayerNormW n3;
+    NodeUpdW nu;
+};
+
+struct DecW {
+    int64_t msg;            // [W1b | W2] KN  (W1b = h_E block of the 512-wide W1)
+    int64_t b1, b2;
+    int64_t W1a, W1d;       // h_V[i] block, h_V[j] block
+    int64_t Tseq;           // [21][128] = W_s . W1c^T : the h_S[j] term folded per letter
+    NodeUpdW nu;
+};
+
+struct DevLayout {
+    int64_t pos_table;      // [66][16]  = embeddings.linear.weight^T + bias
+    int64_t feat;           // [edge_embedding KN (416 rows) | W_e KN (128 rows)] 17 chunks
+    int64_t be;             // W_e bias
+    LayerNormW ne;          // norm_edges
+    int64_t rbf_mu;         // [16]
+    EncW enc[3];
+    DecW dec[3];
+    int64_t Ws;             // [21][128] embedding rows
+    int64_t la, la_b;       // KN [384][384], [384]
+    int64_t m1, m1_b;       // KN [384][64]
+    int64_t m2, m2_b;       // KN [64][32]
+    int64_t m3, m3_b;       // KN [32][21]
+    int64_t ddg;            // [2] = scale, shift
+    int64_t zeros;          // [128] zeros (Q for the first encoder layer)
+    int64_t total;
+};
+
+}  // namespace tmpnn

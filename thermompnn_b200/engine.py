@@ -1,0 +1,176 @@
+"""ctypes binding of the C ABI in ``include/thermompnn_b200.h``.
+
+This is the only door into the CUDA path.  There is deliberately no fallback:
+if the shared library is missing or no B200 is visible, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libthermompnn_b200.so")
+
+IN_DEVICE, OUT_DEVICE, NO_SYNC = 1, 2, 4
+
+# every symbol include/thermompnn_b200.h declares
+SYMBOLS = [
+    "tmpnn_abi_version", "tmpnn_create", "tmpnn_destroy", "tmpnn_last_error", "tmpnn_weight_count",
+    "tmpnn_weight_info", "tmpnn_weight_blob_floats", "tmpnn_load_weights", "tmpnn_run_batch", "tmpnn_fetch",
+    "tmpnn_set_debug_stop", "tmpnn_set_profiling", "tmpnn_profile_count", "tmpnn_profile_get",
+    "tmpnn_profile_reset", "tmpnn_launch_count",
+]
+
+_lib = None
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def load_library() -> C.CDLL:
+    """dlopen the in-tree library and declare prototypes.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EngineError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). thermompnn_b200 has no CPU or eager fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, u32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32
+    lib.tmpnn_abi_version.restype = C.c_int
+    lib.tmpnn_create.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.tmpnn_destroy.argtypes = [vp]
+    lib.tmpnn_destroy.restype = None
+    lib.tmpnn_last_error.argtypes = [vp]
+    lib.tmpnn_last_error.restype = C.c_char_p
+    lib.tmpnn_weight_count.restype = C.c_int
+    lib.tmpnn_weight_info.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(i64), C.POINTER(i32), C.POINTER(i32)]
+    lib.tmpnn_weight_blob_floats.restype = i64
+    lib.tmpnn_load_weights.argtypes = [vp, vp, i64]
+    lib.tmpnn_run_batch.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, u32, vp]
+    lib.tmpnn_fetch.argtypes = [vp, C.c_char_p, vp, i64]
+    lib.tmpnn_set_debug_stop.argtypes = [vp, C.c_int]
+    lib.tmpnn_set_profiling.argtypes = [vp, C.c_int]
+    lib.tmpnn_profile_count.argtypes = [vp]
+    lib.tmpnn_profile_get.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(i64)]
+    lib.tmpnn_profile_reset.argtypes = [vp]
+    lib.tmpnn_launch_count.argtypes = [vp]
+    lib.tmpnn_launch_count.restype = i64
+    _lib = lib
+    return lib
+
+
+def weight_table() -> List[Tuple[str, int, int, int]]:
+    """[(name, offset, rows, cols)] of the raw checkpoint contract (no GPU needed)."""
+    lib = load_library()
+    out = []
+    for i in range(lib.tmpnn_weight_count()):
+        name, off, r, c = C.c_char_p(), C.c_int64(), C.c_int32(), C.c_int32()
+        lib.tmpnn_weight_info(i, C.byref(name), C.byref(off), C.byref(r), C.byref(c))
+        out.append((name.value.decode(), off.value, r.value, c.value))
+    return out
+
+
+def pack_weight_blob(state: Dict[str, np.ndarray]) -> np.ndarray:
+    """Pack a reference state_dict (``model.`` prefix stripped) into the blob ``tmpnn_load_weights`` takes."""
+    lib = load_library()
+    blob = np.zeros(lib.tmpnn_weight_blob_floats(), dtype=np.float32)
+    for name, off, r, c in weight_table():
+        if name not in state:
+            raise KeyError(f"checkpoint is missing tensor '{name}'")
+        v = np.asarray(state[name], dtype=np.float32)
+        if v.size != r * c:
+            raise ValueError(f"tensor '{name}' has {v.size} elements, expected {r}x{c}")
+        blob[off:off + r * c] = v.reshape(-1)
+    return blob
+
+
+def _ptr(a) -> int:
+    return a.ctypes.data if isinstance(a, np.ndarray) else int(a)
+
+
+class Engine:
+    """One GPU's ThermoMPNN engine (wraps a ``tmpnn_ctx``)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load_library()
+        self._ctx = C.c_void_p()
+        rc = self._lib.tmpnn_create(device, C.byref(self._ctx))
+        if rc != 0:
+            raise EngineError(self._lib.tmpnn_last_error(None).decode())
+        self.device = device
+        self._n_last = 0
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx:
+            self._lib.tmpnn_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    __del__ = close
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise EngineError(f"[{rc}] " + self._lib.tmpnn_last_error(self._ctx).decode())
+
+    def load_weights(self, blob: np.ndarray):
+        blob = np.ascontiguousarray(blob, dtype=np.float32)
+        self._check(self._lib.tmpnn_load_weights(self._ctx, blob.ctypes.data, blob.size))
+
+    def run(self, offsets: np.ndarray, X, S, residue_idx, chain_enc, mask, out=None, *, flags: int = 0,
+            stream: int = 0):
+        """Run one ragged batch.  With flags == 0 every array is a host numpy array (``offsets`` always is);
+        with IN_DEVICE / OUT_DEVICE pass raw device pointers (ints) for the inputs / ``out``."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.int32)
+        B, N = offsets.size - 1, int(offsets[-1])
+        if not (flags & IN_DEVICE):
+            X = np.ascontiguousarray(X, dtype=np.float32)
+            S = np.ascontiguousarray(S, dtype=np.int32)
+            residue_idx = np.ascontiguousarray(residue_idx, dtype=np.int32)
+            chain_enc = np.ascontiguousarray(chain_enc, dtype=np.int32)
+            mask = np.ascontiguousarray(mask, dtype=np.uint8)
+            if not (X.size == N * 12 and S.size == N and residue_idx.size == N and chain_enc.size == N and mask.size == N):
+                raise ValueError("input array sizes do not match offsets[-1]")
+        if out is None:
+            if flags & OUT_DEVICE:
+                raise ValueError("OUT_DEVICE needs an explicit device pointer")
+            out = np.empty((N, 21), dtype=np.float32)
+        self._check(self._lib.tmpnn_run_batch(self._ctx, B, offsets.ctypes.data, _ptr(X), _ptr(S), _ptr(residue_idx),
+                                              _ptr(chain_enc), _ptr(mask), _ptr(out), flags, stream or None))
+        self._n_last = N
+        return out
+
+    # ---- introspection ----------------------------------------------------
+    _SHAPES = {"E_idx": ((48,), np.int32), "D_nb": ((48,), np.float32), "h_E": ((48, 128), np.float32),
+               "h_V": ((128,), np.float32), "dec1": ((128,), np.float32), "dec2": ((128,), np.float32),
+               "table": ((21,), np.float32)}
+
+    def fetch(self, name: str) -> np.ndarray:
+        shape, dt = self._SHAPES[name]
+        a = np.empty((self._n_last,) + shape, dtype=dt)
+        self._check(self._lib.tmpnn_fetch(self._ctx, name.encode(), a.ctypes.data, a.nbytes))
+        return a
+
+    def set_debug_stop(self, stage: int):
+        self._check(self._lib.tmpnn_set_debug_stop(self._ctx, stage))
+
+    def set_profiling(self, on: bool):
+        self._check(self._lib.tmpnn_set_profiling(self._ctx, int(on)))
+
+    def profile_reset(self):
+        self._check(self._lib.tmpnn_profile_reset(self._ctx))
+
+    def profile(self) -> Dict[str, Tuple[float, int]]:
+        out = {}
+        for i in range(self._lib.tmpnn_profile_count(self._ctx)):
+            name, ms, n = C.c_char_p(), C.c_double(), C.c_int64()
+            self._lib.tmpnn_profile_get(self._ctx, i, C.byref(name), C.byref(ms), C.byref(n))
+            out[name.value.decode()] = (ms.value, n.value)
+        return out
+
+    def launch_count(self) -> int:
+        return int(self._lib.tmpnn_launch_count(self._ctx))
