@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py -- site-saturation ddG throughput of the CUDA path (and of the CPU reference arm).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c5] [--impl ours|reference]
+
+One "step" = one pass of the whole hot path (k-NN graph -> edge features -> 3 Enc + 3 Dec layers ->
+head table for all 21 letters) over one batch of synthetic proteins.  Default workload = BASELINE.json
+configs[1]: one 300-residue synthetic protein, 6000 residue-mutations per step.  With N GPUs every rank
+runs its own copy of the workload (weak scaling) and the per-protein tables are all-gathered with one NCCL
+collective inside the timed step.  Prints ONE JSON line on rank 0.
+
+  value      mutations/s with inputs already resident in HBM (device pointers into the C ABI), CUDA-event time
+  e2e        the same metric through the C ABI with pinned HOST buffers: H2D of the packed inputs and D2H of
+             the [N,21] table inside the timed region
+  roofline   dominant kernel, per-launch CUDA-event time measured live by the engine's profiling hooks
+  cpu_baseline / --impl reference: the oracle's restatement of the reference's CPU path (torch ops, per-mutation
+             head loop exactly as upstream), timed on this box's host cores
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+CKPT = os.path.join(ROOT, "tests", "golden", "thermompnn_default_slim.npz")
+METRIC = "residue-mutations/sec (site-saturation ddG)"
+
+# algorithmic work of the reference formulation, per kernel class, per edge / per residue
+ALGO = {  # name: (flop_per_edge, flop_per_node, bytes_per_edge, bytes_per_node)
+    "edge_feat": (2 * 416 * 128 + 2 * 128 * 128, 0, 512 + 4, 15 * 4),
+    "enc_msg": (2 * (384 + 128 + 128) * 128, 0, 512 + 4, 1024),
+    "dec_msg": (2 * (512 + 128 + 128) * 128, 0, 512 + 4, 1024),
+    "edge_upd": (2 * (384 + 128 + 128) * 128, 0, 1024 + 4, 512),
+    "node_update": (0, 2 * 2 * 128 * 512, 0, 1024 + 4 * 512),
+    "head": (0, 349504, 0, 3 * 512 + 84),
+    "knn": (0, 0, 8, 64),
+    "prep_nodes": (0, 0, 0, 112),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained"),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def make_workload(name, rank):
+    from thermompnn_b200 import synth
+    if name == "c2":
+        return [synth.synth(300, seed=rank)], "BASELINE configs[1]: one 300-residue synthetic protein, full 20-AA scan"
+    if name == "c3":
+        pdbs = synth.config3()
+        if rank:
+            pdbs = [synth.synth(len(p["seq"]), seed=100000 * rank + i) for i, p in enumerate(pdbs)]
+        return pdbs, "BASELINE configs[2]: 256 synthetic proteins, lengths U[150,500] (seed 1234)"
+    if name == "c5":
+        return [synth.synth(2000, seed=2000 + 8 * rank + i) for i in range(8)], "BASELINE configs[4] per-GPU share: 8 synthetic proteins of 2000 residues"
+    raise SystemExit(f"unknown workload {name}")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def result(self):
+        self.stop_flag = True
+        if self.is_alive():
+            self.join(timeout=1.0)
+        s = self.samples
+        return {"sm_mhz": statistics.median(s) if s else None, "sm_max_mhz": self.max_mhz, "samples": len(s),
+                "reasons": sorted(self.reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle's port of TransferModel.forward on host cores
+# ---------------------------------------------------------------------------------------------
+def reference_weights():
+    import torch
+    from oracle import thermompnn_oracle as O
+    w = O.cast_weights(dict(np.load(CKPT)))
+    # The per-mutation loop needs the full k=9 convolutions.  Off-centre taps and the attention branch cannot
+    # influence the result on a length-1 sequence (tests/test_oracle.py), so they are filled with noise here.
+    g = torch.Generator().manual_seed(0)
+    full = torch.randn(384, 384, 9, generator=g) * 0.02
+    full[:, :, 4] = w["light_attention.feature_convolution.weight_center"]
+    w["light_attention.feature_convolution.weight"] = full
+    w["light_attention.attention_convolution.weight"] = torch.randn(384, 384, 9, generator=g) * 0.02
+    w["light_attention.attention_convolution.bias"] = torch.zeros(384)
+    return w
+
+
+def time_reference_step(w, pdb, n_sample):
+    """One bounded sample of the reference CPU path on `pdb`: the full ProteinMPNN pass plus `n_sample` iterations
+    of the per-mutation head loop; returns the full-protein time estimate t_mpnn + t_head * (n_total / n_sample)."""
+    import torch
+    from oracle import thermompnn_oracle as O
+    X, S, mask, ridx, cenc = O.featurize(pdb)
+    L = len(S)
+    n_total = 20 * int((np.asarray(list(pdb["seq"])) != "-").sum())
+    rng = np.random.default_rng(0)
+    pos = rng.integers(0, L, size=n_sample)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        hidden, h_S = O.mpnn_forward(w, torch.from_numpy(X), torch.from_numpy(S), torch.from_numpy(mask),
+                                     torch.from_numpy(ridx), torch.from_numpy(cenc))
+        t1 = time.perf_counter()
+        for k in range(n_sample):
+            p = int(pos[k])
+            O.head_per_mutation(w, hidden, h_S, p, int(S[p]), k % 20)
+        t2 = time.perf_counter()
+    return (t1 - t0) + (t2 - t1) * (n_total / n_sample), n_total, (t1 - t0), (t2 - t1)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import torch
+    pdbs, desc = make_workload(args.workload, 0)
+    pdbs = pdbs[:4]   # bounded: at most four proteins of the batch per step
+    w = reference_weights()
+    cores = torch.get_num_threads()
+    n_sample = 300
+    times, muts = [], 0
+    for it in range(args.warmup + args.steps):
+        t, m = 0.0, 0
+        for pdb in pdbs:
+            tt, n_total, _, _ = time_reference_step(w, pdb, n_sample)
+            t += tt
+            m += n_total
+        if it >= args.warmup:
+            times.append(t)
+            muts = m
+    ms = 1e3 * sum(times) / len(times)
+    value = muts / (ms / 1e3)
+    sample = (f"per step: full ProteinMPNN pass + {n_sample} of {muts // len(pdbs)} per-mutation head iterations per protein on "
+              f"{len(pdbs)} protein(s), head time scaled to the full mutation list")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "mutations/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": desc, "host": "cpu"},
+        "cpu_baseline": {"value": value, "unit": "mutations/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "mutations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from thermompnn_b200 import engine as E
+    from thermompnn_b200.featurize import featurize_batch
+    from thermompnn_b200.weights import load_state, random_state
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    eng = E.Engine(local_rank)
+    real_weights = os.path.exists(CKPT)
+    eng.load_weights(E.pack_weight_blob(load_state(CKPT) if real_weights else random_state(0)))
+
+    pdbs, desc = make_workload(args.workload, rank)
+    p = featurize_batch(pdbs)
+    N, B = p.n_residues, p.n_proteins
+    n_mut = 20 * N                       # synthetic proteins have no gaps: 20 substitutions per residue
+    n_edges = int(sum(min(48, int(l)) * int(l) for l in np.diff(p.offsets)))
+
+    # device-resident inputs (value) and pinned host inputs (e2e)
+    d = {k: torch.from_numpy(np.ascontiguousarray(getattr(p, k))).to(dev) for k in ("X", "S", "residue_idx", "chain_enc", "mask")}
+    d_out = torch.empty((N, 21), dtype=torch.float32, device=dev)
+    h = {k: torch.from_numpy(np.ascontiguousarray(getattr(p, k))).pin_memory() for k in ("X", "S", "residue_idx", "chain_enc", "mask")}
+    h_out = torch.empty((N, 21), dtype=torch.float32).pin_memory()
+    gather = [torch.empty_like(d_out) for _ in range(world)] if world > 1 else None
+    flush_buf = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+    st = torch.cuda.Stream(device=dev)
+    sh = st.cuda_stream
+    DEV = E.IN_DEVICE | E.OUT_DEVICE | E.NO_SYNC
+
+    def step_device():
+        eng.run(p.offsets, d["X"].data_ptr(), d["S"].data_ptr(), d["residue_idx"].data_ptr(), d["chain_enc"].data_ptr(),
+                d["mask"].data_ptr(), d_out.data_ptr(), flags=DEV, stream=sh)
+        if world > 1:
+            dist.all_gather(gather, d_out)
+
+    def step_host():
+        eng.run(p.offsets, h["X"].numpy(), h["S"].numpy(), h["residue_idx"].numpy(), h["chain_enc"].numpy(), h["mask"].numpy(),
+                h_out.numpy(), stream=sh)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    with torch.cuda.stream(st):
+        # ---- warm-up ------------------------------------------------------------------------
+        for _ in range(max(args.warmup, 3)):
+            flush_buf.zero_()
+            step_device()
+        barrier()
+        step_host()
+        barrier()
+
+        # ---- value: device-resident inputs, CUDA events per step, L2 flushed between steps --------
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        eng.profile_reset()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        barrier()
+        t_wall0 = time.perf_counter()
+        for a, b in ev:
+            flush_buf.zero_()
+            a.record(st)
+            step_device()
+            b.record(st)
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+        launches = eng.launch_count()
+        clocks = sampler.result()
+        dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+        dev_ms = max_over_ranks(dev_ms)
+        ms_per_step = dev_ms / args.steps
+        value = world * n_mut / (ms_per_step / 1e3)
+
+        # ---- e2e: pinned host buffers through the C ABI, copies inside the timed region -----------
+        e2e_t = []
+        barrier()
+        for _ in range(args.steps):
+            flush_buf.zero_()
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            step_host()
+            e2e_t.append(time.perf_counter() - t0)
+        barrier()
+        e2e_ms = max_over_ranks(1e3 * sum(e2e_t) / len(e2e_t))
+        e2e_value = world * n_mut / (e2e_ms / 1e3)
+        h2d = 4 * (B + 1) + N * (48 + 4 + 4 + 4 + 1)
+        d2h = N * 21 * 4
+
+        # ---- roofline: per-kernel CUDA-event durations, same steps, L2 flushed ----------------------
+        eng.set_profiling(True)
+        eng.profile_reset()
+        prof_steps = min(args.steps, 20)
+        for _ in range(prof_steps):
+            flush_buf.zero_()
+            step_device()
+        torch.cuda.synchronize(dev)
+        prof = eng.profile()
+        eng.set_profiling(False)
+
+    if rank == 0:
+        peaks = load_peaks()
+        tot = sum(v[0] for v in prof.values())
+        kern = {}
+        for k, (ms, n) in prof.items():
+            per_launch_ms = ms / max(n, 1)
+            fe, fn, be, bn = ALGO[k]
+            kern[k] = {"us_per_launch": 1e3 * per_launch_ms, "launches_per_step": n // prof_steps, "share": ms / tot,
+                       "algo_tflops": (fe * n_edges + fn * N) / (per_launch_ms * 1e-3) / 1e12,
+                       "algo_gbs": (be * n_edges + bn * N) / (per_launch_ms * 1e-3) / 1e9}
+        top = max(("edge_upd", "enc_msg", "dec_msg", "edge_feat"), key=lambda k: prof.get(k, (0, 0))[0])
+        tk = kern[top]
+        roofline = {"kernel": top, "bound": "tensor", "achieved": tk["algo_tflops"], "peak": peaks["bf16_tflops"],
+                    "unit": "TFLOP/s", "frac": tk["algo_tflops"] / peaks["bf16_tflops"], "traffic": None,
+                    "peak_source": peaks["source"] + ", dense bf16 burst",
+                    "note": "fp32-accurate path; algorithmic FLOPs of the reference formulation (SURVEY 8d). FP32 SIMT generation: "
+                            "no tensor-core instructions yet, so frac is against a peak this kernel cannot reach",
+                    "hbm": {"achieved": tk["algo_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": tk["algo_gbs"] / peaks["hbm_gbs"]},
+                    "us_per_launch": tk["us_per_launch"], "share_of_step": tk["share"]}
+        # cpu baseline on a bounded sample (rank 0, N=1 only)
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            import torch as _t
+            w = reference_weights()
+            ts = [time_reference_step(w, pdbs[i % len(pdbs)], 300) for i in range(3)]
+            est = statistics.median(t[0] for t in ts)
+            cpu = {"value": ts[0][1] / est, "unit": "mutations/s", "cores": _t.get_num_threads(), "kind": "port",
+                   "sample": "3 runs on one protein of the workload: full ProteinMPNN pass + 300 per-mutation head iterations, "
+                             "head time scaled to the full list; median",
+                   "mpnn_s": statistics.median(t[2] for t in ts)}
+        out = {
+            "metric": METRIC, "value": value, "unit": "mutations/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic coordinates (thermompnn_b200.synth), " + ("reference checkpoint weights" if real_weights else "random-init weights"),
+            "config": {"workload": desc, "proteins_per_gpu": B, "residues_per_gpu": N, "edges_per_gpu": n_edges, "k_neighbors": 48,
+                       "hidden": 128, "l2": "flushed between timed steps (256 MB write)", "parallelism": f"dp{world}"},
+            "e2e": {"value": e2e_value, "unit": "mutations/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "launches_per_step": int(launches) // args.steps,
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "kernels": kern,
+            "wall_s_timed_region": t_wall,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -22,7 +22,8 @@
  * (the reference itself is strictly B=1; a batch here is defined as "identical
  * to running each protein alone"):
  *
- *   offsets[B+1]   int32   node range of protein b is [offsets[b], offsets[b+1]);  N = offsets[B]
+ *   offsets[B+1]   int32   node range of protein b is [offsets[b], offsets[b+1]);  N = offsets[B].
+ *                          ALWAYS a host pointer (the host sizes grids from it), even with TMPNN_IN_DEVICE
  *   X[N][4][3]     float   backbone N, CA, C, O; zeros where the residue is missing
  *   S[N]           int32   residue letter index in "ACDEFGHIKLMNPQRSTVWYX"
  *   residue_idx[N] int32   100*(chain-1) + position
@@ -61,7 +62,7 @@ extern "C" {
 #define TMPNN_E_RANGE      -5   /* S / chain / buffer size out of range */
 
 /* tmpnn_run_batch flags */
-#define TMPNN_IN_DEVICE    1u   /* all input pointers are device pointers on the context's device */
+#define TMPNN_IN_DEVICE    1u   /* X, S, residue_idx, chain_enc, mask are device pointers on the context's device */
 #define TMPNN_OUT_DEVICE   2u   /* out_table is a device pointer */
 #define TMPNN_NO_SYNC      4u   /* do not synchronise the stream before returning (device in/out only) */
 

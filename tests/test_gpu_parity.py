@@ -53,8 +53,8 @@ def test_layerwise(name, gpu_model):
         assert (E_idx[valid][:, 0] == np.arange(L)[valid]).all()          # self first
         # h_E after W_e, compared slot-by-slot where the order agrees
         hE = eng.fetch("h_E")[:6, :K]
-        same = E_idx[:6, :K] == d["E_idx"][:6]
-        assert same.mean() > 0.9
+        same = (E_idx[:6, :K] == d["E_idx"][:6]) & valid[:6, None]   # gap rows pick arbitrary (all-tie) neighbours
+        assert same[valid[:6]].mean() > 0.9
         assert np.abs(hE - d["h_E0_head"])[same].max() <= 2e-5
         for l in range(3):
             eng.set_debug_stop(3 + l)

@@ -68,6 +68,8 @@ struct tmpnn_ctx {
     DevBuf<unsigned char> d_in;
     unsigned char* h_stage = nullptr;
     size_t h_stage_cap = 0;
+    cudaEvent_t stage_ev = nullptr;   // completion of the last H2D out of h_stage
+    bool stage_busy = false;
     // per-node
     DevBuf<int> pstart, pend;
     DevBuf<float> atoms, maskf, hV, dec_prev, dec_last, Ssum, cnt, P, Q, P2, Q2, table;
@@ -143,17 +145,38 @@ struct Prep {
         return off;
     }
     LayerNormW ln(const std::string& p) { return {vec(p + ".weight"), vec(p + ".bias")}; }
-    NodeUpdW node_upd(const std::string& p) {
+    // projections: (weight name, first input column) pairs appended to the layer's stream
+    NodeUpdW node_upd(const std::string& p, const std::vector<std::pair<std::string, int>>& projs) {
         NodeUpdW w;
-        w.W3 = kn(p + "W3.weight");
+        w.nchunks = 4 + 16 + 16 + 4 * (int)projs.size();
+        w.stream = alloc((int64_t)w.nchunks * 4096);
+        int64_t o = w.stream;
+        put_kn(o, p + "W3.weight", 0, HID); o += HID * HID;
+        {   // W_in [512][128] -> four [128 k][128 n] column blocks
+            const float* W = find(p + "dense.W_in.weight");
+            for (int blk = 0; blk < 4; ++blk, o += HID * HID)
+                for (int k = 0; k < HID; ++k)
+                    for (int n = 0; n < HID; ++n) dev[o + (int64_t)k * HID + n] = W[(int64_t)(blk * HID + n) * HID + k];
+        }
+        put_kn(o, p + "dense.W_out.weight", 0, 4 * HID); o += 4 * HID * HID;
+        for (auto& pr : projs) { put_kn(o, pr.first, pr.second, HID); o += HID * HID; }
         w.b3 = vec(p + "W3.bias");
         w.n1 = ln(p + "norm1");
         w.n2 = ln(p + "norm2");
-        w.Win = kn(p + "dense.W_in.weight");
         w.bin = vec(p + "dense.W_in.bias");
-        w.Wout = kn(p + "dense.W_out.weight");
         w.bout = vec(p + "dense.W_out.bias");
         return w;
+    }
+    // KN of an nn.Linear [out][in] padded to 128 output columns, appended at off; returns floats written
+    int64_t put_kn_padded(int64_t off, const std::string& name, int col0, int ncols_out_begin, int k_rows) {
+        int out, in;
+        const float* W = find(name, &out, &in);
+        for (int k = 0; k < k_rows; ++k)
+            for (int n = 0; n < HID; ++n) {
+                int oc = ncols_out_begin + n;
+                dev[off + (int64_t)k * HID + n] = (oc < out && col0 + k < in) ? W[(int64_t)oc * in + col0 + k] : 0.f;
+            }
+        return (int64_t)k_rows * HID;
     }
 };
 
@@ -187,8 +210,6 @@ DevLayout prepare_weights(Prep& P) {
         P.put_kn(e.msg + HID * HID, p + "W2.weight", 0, HID);
         e.b1 = P.vec(p + "W1.bias");
         e.b2 = P.vec(p + "W2.bias");
-        e.W1a = P.kn(p + "W1.weight", 0, HID);
-        e.W1c = P.kn(p + "W1.weight", 2 * HID, HID);
         e.edge = P.alloc(3 * HID * HID);
         P.put_kn(e.edge, p + "W11.weight", HID, HID);
         P.put_kn(e.edge + HID * HID, p + "W12.weight", 0, HID);
@@ -196,10 +217,20 @@ DevLayout prepare_weights(Prep& P) {
         e.b11 = P.vec(p + "W11.bias");
         e.b12 = P.vec(p + "W12.bias");
         e.b13 = P.vec(p + "W13.bias");
-        e.W11a = P.kn(p + "W11.weight", 0, HID);
-        e.W11c = P.kn(p + "W11.weight", 2 * HID, HID);
         e.n3 = P.ln(p + "norm3");
-        e.nu = P.node_upd(p);
+        {   // projections gathered by this layer's edge update and by the next message kernel
+            std::vector<std::pair<std::string, int>> pr = {{p + "W11.weight", 0}, {p + "W11.weight", 2 * HID}};
+            if (l < 2) {
+                const std::string nx = pm + "encoder_layers." + std::to_string(l + 1) + ".";
+                pr.push_back({nx + "W1.weight", 0});
+                pr.push_back({nx + "W1.weight", 2 * HID});
+            } else {
+                const std::string nx = pm + "decoder_layers.0.";
+                pr.push_back({nx + "W1.weight", 0});
+                pr.push_back({nx + "W1.weight", 3 * HID});
+            }
+            e.nu = P.node_upd(p, pr);
+        }
     }
     const float* Ws = P.find(pm + "W_s.weight");
     for (int l = 0; l < 3; ++l) {
@@ -210,8 +241,6 @@ DevLayout prepare_weights(Prep& P) {
         P.put_kn(d.msg + HID * HID, p + "W2.weight", 0, HID);
         d.b1 = P.vec(p + "W1.bias");
         d.b2 = P.vec(p + "W2.bias");
-        d.W1a = P.kn(p + "W1.weight", 0, HID);
-        d.W1d = P.kn(p + "W1.weight", 3 * HID, HID);
         // h_S[j] term: W1[:, 256:384] . W_s[S_j]  -> one row per letter
         const float* W1 = P.find(p + "W1.weight");
         d.Tseq = P.alloc(21 * HID);
@@ -221,14 +250,29 @@ DevLayout prepare_weights(Prep& P) {
                 for (int k = 0; k < HID; ++k) s += (double)Ws[a * HID + k] * (double)W1[(int64_t)n * 4 * HID + 2 * HID + k];
                 P.dev[d.Tseq + a * HID + n] = (float)s;
             }
-        d.nu = P.node_upd(p);
+        {
+            std::vector<std::pair<std::string, int>> pr;
+            if (l < 2) {
+                const std::string nx = pm + "decoder_layers." + std::to_string(l + 1) + ".";
+                pr = {{nx + "W1.weight", 0}, {nx + "W1.weight", 3 * HID}};
+            }
+            d.nu = P.node_upd(p, pr);
+        }
     }
     L.Ws = P.vec(pm + "W_s.weight");
-    L.la = P.kn("light_attention.feature_convolution.weight_center");
+    {
+        L.head = P.alloc((int64_t)51 * 4096);
+        int64_t o = L.head;
+        for (int blk = 0; blk < 3; ++blk)
+            o += P.put_kn_padded(o, "light_attention.feature_convolution.weight_center", 0, blk * HID, 3 * HID);
+        o += P.put_kn_padded(o, "both_out.1.weight", 0, 0, 3 * HID);
+        o += P.put_kn_padded(o, "both_out.3.weight", 0, 0, 64);
+        o += P.put_kn_padded(o, "both_out.5.weight", 0, 0, 32);
+    }
     L.la_b = P.vec("light_attention.feature_convolution.bias");
-    L.m1 = P.kn("both_out.1.weight"); L.m1_b = P.vec("both_out.1.bias");
-    L.m2 = P.kn("both_out.3.weight"); L.m2_b = P.vec("both_out.3.bias");
-    L.m3 = P.kn("both_out.5.weight"); L.m3_b = P.vec("both_out.5.bias");
+    L.m1_b = P.vec("both_out.1.bias");
+    L.m2_b = P.vec("both_out.3.bias");
+    L.m3_b = P.vec("both_out.5.bias");
     L.ddg = P.alloc(2);
     P.dev[L.ddg] = *P.find("ddg_out.weight");
     P.dev[L.ddg + 1] = *P.find("ddg_out.bias");
@@ -377,6 +421,7 @@ int tmpnn_create(int device, tmpnn_ctx** out) {
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess)
         return bail(std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
     if ((e = kernels_init()) != cudaSuccess) return bail(std::string("kernels_init: ") + cudaGetErrorString(e));
+    if ((e = node_kernels_init()) != cudaSuccess) return bail(std::string("node_kernels_init: ") + cudaGetErrorString(e));
     *out = ctx;
     return TMPNN_OK;
 }
@@ -387,6 +432,7 @@ void tmpnn_destroy(tmpnn_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     drain_profile(ctx);
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
+    if (ctx->stage_ev) cudaEventDestroy(ctx->stage_ev);
     if (ctx->d_weights) cudaFree(ctx->d_weights);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     ctx->d_in.release();
@@ -455,6 +501,10 @@ int tmpnn_run_batch(tmpnn_ctx* ctx, int32_t B, const int32_t* offsets, const flo
     const size_t o_m = align16(o_c + (size_t)N * 4);
     const size_t in_bytes = align16(o_m + (size_t)N);
     const size_t used = in_dev ? align16((size_t)(B + 1) * 4) : in_bytes;
+    if (ctx->stage_busy) {   // a previous TMPNN_NO_SYNC call may still be reading the staging buffer
+        CU(cudaEventSynchronize(ctx->stage_ev));
+        ctx->stage_busy = false;
+    }
     CU(ctx->d_in.reserve(used));
     if (ctx->h_stage_cap < used) {
         if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
@@ -481,6 +531,9 @@ int tmpnn_run_batch(tmpnn_ctx* ctx, int32_t B, const int32_t* offsets, const flo
         d_m = ctx->d_in.p + o_m;
     }
     CU(cudaMemcpyAsync(ctx->d_in.p, ctx->h_stage, used, cudaMemcpyHostToDevice, st));
+    if (!ctx->stage_ev) CU(cudaEventCreateWithFlags(&ctx->stage_ev, cudaEventDisableTiming));
+    CU(cudaEventRecord(ctx->stage_ev, st));
+    ctx->stage_busy = true;
 
     // ---- buffers --------------------------------------------------------------
     const size_t n = (size_t)N, ne = n * KNB;
@@ -529,19 +582,19 @@ int tmpnn_run_batch(tmpnn_ctx* ctx, int32_t B, const int32_t* offsets, const flo
             NodeUpdArgs a{};
             a.weights = W; a.w = e.nu; a.Ssum = ctx->Ssum.p; a.cnt = ctx->cnt.p; a.hV = ctx->hV.p; a.hV_copy = nullptr;
             a.maskf = ctx->maskf.p; a.S = d_S; a.N = N;
-            a.proj[0] = {e.W11a, e.b11, -1, ctx->P2.p};     // edge update of this layer
-            a.proj[1] = {e.W11c, -1, -1, ctx->Q2.p};
+            a.proj[0] = {e.b11, -1, ctx->P2.p};     // edge update of this layer
+            a.proj[1] = {-1, -1, ctx->Q2.p};
             if (l < 2) {
                 const EncW& nx = L.enc[l + 1];
-                a.proj[2] = {nx.W1a, nx.b1, -1, ctx->P.p};
-                a.proj[3] = {nx.W1c, -1, -1, ctx->Q.p};
+                a.proj[2] = {nx.b1, -1, ctx->P.p};
+                a.proj[3] = {-1, -1, ctx->Q.p};
             } else {
                 const DecW& nx = L.dec[0];
-                a.proj[2] = {nx.W1a, nx.b1, -1, ctx->P.p};
-                a.proj[3] = {nx.W1d, -1, nx.Tseq, ctx->Q.p};
+                a.proj[2] = {nx.b1, -1, ctx->P.p};
+                a.proj[3] = {-1, nx.Tseq, ctx->Q.p};
             }
             a.nproj = 4;
-            { LaunchScope ls(ctx, st, "node_update"); launch_node_update(a, st); }
+            { LaunchScope ls(ctx, st, "node_update"); launch_node_update(a, ctx->sm_count, st); }
             { LaunchScope ls(ctx, st, "edge_upd");
               launch_edge_upd(npt, ctx->hE.p, ctx->E_idx.p, ctx->P2.p, ctx->Q2.p, W + e.edge, W + e.b12, W + e.b13,
                               W + e.n3.g, W + e.n3.b, N, st); }
@@ -561,18 +614,18 @@ int tmpnn_run_batch(tmpnn_ctx* ctx, int32_t B, const int32_t* offsets, const flo
             a.nproj = 0;
             if (l < 2) {
                 const DecW& nx = L.dec[l + 1];
-                a.proj[0] = {nx.W1a, nx.b1, -1, ctx->P.p};
-                a.proj[1] = {nx.W1d, -1, nx.Tseq, ctx->Q.p};
+                a.proj[0] = {nx.b1, -1, ctx->P.p};
+                a.proj[1] = {-1, nx.Tseq, ctx->Q.p};
                 a.nproj = 2;
             }
-            { LaunchScope ls(ctx, st, "node_update"); launch_node_update(a, st); }
+            { LaunchScope ls(ctx, st, "node_update"); launch_node_update(a, ctx->sm_count, st); }
             stage_done(6 + l);
         }
     }
     if (!done) {
         HeadArgs h{};
-        h.weights = W; h.Ws = L.Ws; h.la = L.la; h.la_b = L.la_b; h.m1 = L.m1; h.m1_b = L.m1_b; h.m2 = L.m2;
-        h.m2_b = L.m2_b; h.m3 = L.m3; h.m3_b = L.m3_b; h.ddg = L.ddg;
+        h.weights = W; h.stream = L.head; h.Ws = L.Ws; h.la_b = L.la_b; h.m1_b = L.m1_b; h.m2_b = L.m2_b;
+        h.m3_b = L.m3_b; h.ddg = L.ddg;
         h.dec_last = ctx->dec_last.p; h.dec_prev = ctx->dec_prev.p; h.S = d_S; h.table = d_table; h.N = N;
         { LaunchScope ls(ctx, st, "head"); launch_head(h, st); }
         if (!out_dev) CU(cudaMemcpyAsync(out_table, d_table, n * 21 * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -580,6 +633,7 @@ int tmpnn_run_batch(tmpnn_ctx* ctx, int32_t B, const int32_t* offsets, const flo
     CU(cudaGetLastError());
     if (!(flags & TMPNN_NO_SYNC) || !out_dev) {
         CU(cudaStreamSynchronize(st));
+        ctx->stage_busy = false;
         if (ctx->profiling) drain_profile(ctx);
     }
     return TMPNN_OK;

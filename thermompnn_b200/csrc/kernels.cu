@@ -421,219 +421,6 @@ edge_upd_kernel(float* __restrict__ hE, const int* __restrict__ E_idx, const flo
 }
 
 // ---------------------------------------------------------------------------
-// node_update: per-residue tail of an Enc/Dec layer plus the projections the next
-// kernels gather.  128 threads = 128 output columns; NT residues per block.
-// ---------------------------------------------------------------------------
-template <int NT>
-__device__ __forceinline__ void block_layernorm(float (&v)[NT], const float* __restrict__ g, const float* __restrict__ b,
-                                                float* red /*[4][NT]*/, int n) {
-    const int w = n >> 5, lane = n & 31;
-    float mean[NT];
-#pragma unroll
-    for (int t = 0; t < NT; ++t) {
-        float s = v[t];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) red[w * NT + t] = s;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int t = 0; t < NT; ++t) mean[t] = (red[t] + red[NT + t] + red[2 * NT + t] + red[3 * NT + t]) * (1.0f / HID);
-    __syncthreads();
-#pragma unroll
-    for (int t = 0; t < NT; ++t) {
-        float d = v[t] - mean[t];
-        float s = d * d;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) red[w * NT + t] = s;
-    }
-    __syncthreads();
-    const float gg = __ldg(g + n), bb = __ldg(b + n);
-#pragma unroll
-    for (int t = 0; t < NT; ++t) {
-        float var = (red[t] + red[NT + t] + red[2 * NT + t] + red[3 * NT + t]) * (1.0f / HID);
-        v[t] = (v[t] - mean[t]) * (1.0f / sqrtf(var + LN_EPS)) * gg + bb;
-    }
-    __syncthreads();
-}
-
-// acc[t] += sum_k x[t][k] * W[k*ldw + col]
-template <int NT>
-__device__ __forceinline__ void gemv_cols(float (&acc)[NT], const float* x, int ldx, int K, const float* __restrict__ W,
-                                          int ldw, int col) {
-#pragma unroll 2
-    for (int k = 0; k < K; k += 4) {
-        float w0 = __ldg(W + (size_t)k * ldw + col), w1 = __ldg(W + (size_t)(k + 1) * ldw + col);
-        float w2 = __ldg(W + (size_t)(k + 2) * ldw + col), w3 = __ldg(W + (size_t)(k + 3) * ldw + col);
-#pragma unroll
-        for (int t = 0; t < NT; ++t) {
-            float4 xv = *reinterpret_cast<const float4*>(x + t * ldx + k);
-            acc[t] = fmaf(xv.x, w0, acc[t]);
-            acc[t] = fmaf(xv.y, w1, acc[t]);
-            acc[t] = fmaf(xv.z, w2, acc[t]);
-            acc[t] = fmaf(xv.w, w3, acc[t]);
-        }
-    }
-}
-
-template <int NT>
-__global__ void __launch_bounds__(128)
-node_update_kernel(NodeUpdArgs a) {
-    __shared__ __align__(16) float x[NT][HID];
-    __shared__ __align__(16) float hid[NT][4 * HID];
-    __shared__ float red[4 * NT];
-    const int n = threadIdx.x;
-    const int node0 = blockIdx.x * NT;
-    const float* wb = a.weights;
-
-#pragma unroll
-    for (int t = 0; t < NT; ++t) {
-        int node = node0 + t;
-        x[t][n] = node < a.N ? a.Ssum[(size_t)node * HID + n] : 0.f;
-    }
-    __syncthreads();
-    float h[NT];
-    {
-        float acc[NT];
-#pragma unroll
-        for (int t = 0; t < NT; ++t) acc[t] = 0.f;
-        gemv_cols<NT>(acc, &x[0][0], HID, HID, wb + a.w.W3, HID, n);
-        const float b3 = __ldg(wb + a.w.b3 + n);
-#pragma unroll
-        for (int t = 0; t < NT; ++t) {
-            int node = node0 + t;
-            float c = node < a.N ? a.cnt[node] : 0.f;
-            float hv = node < a.N ? a.hV[(size_t)node * HID + n] : 0.f;
-            h[t] = hv + fmaf(c, b3, acc[t]) / MSG_SCALE;
-        }
-    }
-    block_layernorm<NT>(h, wb + a.w.n1.g, wb + a.w.n1.b, red, n);   // ends with a barrier: x is free
-#pragma unroll
-    for (int t = 0; t < NT; ++t) x[t][n] = h[t];
-    __syncthreads();
-    {   // FFN 128 -> 512 -> 128
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float acc[NT];
-            const float bi = __ldg(wb + a.w.bin + n + j * HID);
-#pragma unroll
-            for (int t = 0; t < NT; ++t) acc[t] = bi;
-            gemv_cols<NT>(acc, &x[0][0], HID, HID, wb + a.w.Win, 4 * HID, n + j * HID);
-#pragma unroll
-            for (int t = 0; t < NT; ++t) hid[t][n + j * HID] = gelu_erf(acc[t]);
-        }
-        __syncthreads();
-        float acc[NT];
-        const float bo = __ldg(wb + a.w.bout + n);
-#pragma unroll
-        for (int t = 0; t < NT; ++t) acc[t] = bo;
-        gemv_cols<NT>(acc, &hid[0][0], 4 * HID, 4 * HID, wb + a.w.Wout, HID, n);
-#pragma unroll
-        for (int t = 0; t < NT; ++t) h[t] += acc[t];
-    }
-    block_layernorm<NT>(h, wb + a.w.n2.g, wb + a.w.n2.b, red, n);
-#pragma unroll
-    for (int t = 0; t < NT; ++t) {
-        int node = node0 + t;
-        float m = node < a.N ? a.maskf[node] : 0.f;
-        h[t] *= m;
-        x[t][n] = h[t];
-        if (node < a.N) {
-            a.hV[(size_t)node * HID + n] = h[t];
-            if (a.hV_copy) a.hV_copy[(size_t)node * HID + n] = h[t];
-        }
-    }
-    __syncthreads();
-    for (int p = 0; p < a.nproj; ++p) {
-        const ProjSpec& ps = a.proj[p];
-        float acc[NT];
-        const float b = ps.bias >= 0 ? __ldg(wb + ps.bias + n) : 0.f;
-#pragma unroll
-        for (int t = 0; t < NT; ++t) acc[t] = b;
-        gemv_cols<NT>(acc, &x[0][0], HID, HID, wb + ps.W, HID, n);
-#pragma unroll
-        for (int t = 0; t < NT; ++t) {
-            int node = node0 + t;
-            if (node < a.N) {
-                float v = acc[t];
-                if (ps.table >= 0) v += __ldg(wb + ps.table + (size_t)a.S[node] * HID + n);
-                ps.out[(size_t)node * HID + n] = v;
-            }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------
-// head: x = [dec3 | dec2 | W_s[S]] -> LightAttention centre tap -> (ReLU, Linear)x3 -> affine  => T[N][21]
-// (transfer_model.py:82-83, 96-116, 140-155)
-// ---------------------------------------------------------------------------
-template <int NT>
-__global__ void __launch_bounds__(128)
-head_kernel(HeadArgs a) {
-    __shared__ __align__(16) float x[NT][3 * HID];
-    __shared__ __align__(16) float y[NT][3 * HID];
-    __shared__ __align__(16) float z1[NT][64];
-    __shared__ __align__(16) float z2[NT][32];
-    const int n = threadIdx.x;
-    const int node0 = blockIdx.x * NT;
-    const float* wb = a.weights;
-#pragma unroll
-    for (int t = 0; t < NT; ++t) {
-        int node = node0 + t;
-        bool ok = node < a.N;
-        x[t][n] = ok ? a.dec_last[(size_t)node * HID + n] : 0.f;
-        x[t][HID + n] = ok ? a.dec_prev[(size_t)node * HID + n] : 0.f;
-        x[t][2 * HID + n] = ok ? __ldg(wb + a.Ws + (size_t)a.S[node] * HID + n) : 0.f;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        float acc[NT];
-        const float b = __ldg(wb + a.la_b + n + j * HID);
-#pragma unroll
-        for (int t = 0; t < NT; ++t) acc[t] = b;
-        gemv_cols<NT>(acc, &x[0][0], 3 * HID, 3 * HID, wb + a.la, 3 * HID, n + j * HID);
-#pragma unroll
-        for (int t = 0; t < NT; ++t) y[t][n + j * HID] = fmaxf(acc[t], 0.f);
-    }
-    __syncthreads();
-    if (n < 64) {
-        float acc[NT];
-        const float b = __ldg(wb + a.m1_b + n);
-#pragma unroll
-        for (int t = 0; t < NT; ++t) acc[t] = b;
-        gemv_cols<NT>(acc, &y[0][0], 3 * HID, 3 * HID, wb + a.m1, 64, n);
-#pragma unroll
-        for (int t = 0; t < NT; ++t) z1[t][n] = fmaxf(acc[t], 0.f);
-    }
-    __syncthreads();
-    if (n < 32) {
-        float acc[NT];
-        const float b = __ldg(wb + a.m2_b + n);
-#pragma unroll
-        for (int t = 0; t < NT; ++t) acc[t] = b;
-        gemv_cols<NT>(acc, &z1[0][0], 64, 64, wb + a.m2, 32, n);
-#pragma unroll
-        for (int t = 0; t < NT; ++t) z2[t][n] = fmaxf(acc[t], 0.f);
-    }
-    __syncthreads();
-    if (n < 21) {
-        float acc[NT];
-        const float b = __ldg(wb + a.m3_b + n);
-#pragma unroll
-        for (int t = 0; t < NT; ++t) acc[t] = b;
-        gemv_cols<NT>(acc, &z2[0][0], 32, 32, wb + a.m3, 21, n);
-        const float sc = __ldg(wb + a.ddg), sh = __ldg(wb + a.ddg + 1);
-#pragma unroll
-        for (int t = 0; t < NT; ++t) {
-            int node = node0 + t;
-            if (node < a.N) a.table[(size_t)node * 21 + n] = fmaf(acc[t], sc, sh);
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
 template <int NPT> static size_t smem_edge_feat() {
@@ -713,16 +500,6 @@ void launch_edge_upd(int npt, float* hE, const int* E_idx, const float* P, const
                      cudaStream_t st) {
     TMPNN_DISPATCH_NPT(npt, (edge_upd_kernel<NPT><<<(N + NPT - 1) / NPT, 128 * NPT, smem_edge_upd<NPT>(), st>>>(
         hE, E_idx, P, Q, wstream, b12, b13, ln_g, ln_b, N)));
-}
-
-void launch_node_update(const NodeUpdArgs& a, cudaStream_t st) {
-    constexpr int NT = 8;
-    node_update_kernel<NT><<<(a.N + NT - 1) / NT, 128, 0, st>>>(a);
-}
-
-void launch_head(const HeadArgs& a, cudaStream_t st) {
-    constexpr int NT = 4;
-    head_kernel<NT><<<(a.N + NT - 1) / NT, 128, 0, st>>>(a);
 }
 
 }  // namespace tmpnn

@@ -7,8 +7,7 @@
 
 namespace tmpnn {
 
-struct ProjSpec {      // out[i] = h_V[i] . W (+ bias) (+ table[S_i])
-    int64_t W;         // KN [128][128], offset into the device weight block
+struct ProjSpec {      // out[i] = h_V[i] . W (+ bias) (+ table[S_i]); W is the next 4 chunks of the layer's stream
     int64_t bias;      // offset or -1
     int64_t table;     // [21][128] offset or -1
     float* out;        // [N][128]
@@ -30,7 +29,7 @@ struct NodeUpdArgs {
 
 struct HeadArgs {
     const float* weights;
-    int64_t Ws, la, la_b, m1, m1_b, m2, m2_b, m3, m3_b, ddg;
+    int64_t stream, Ws, la_b, m1_b, m2_b, m3_b, ddg;
     const float* dec_last;  // [N][128] output of the last decoder layer
     const float* dec_prev;  // [N][128] output of the one before
     const int* S;
@@ -39,6 +38,7 @@ struct HeadArgs {
 };
 
 cudaError_t kernels_init();
+cudaError_t node_kernels_init();
 int knn_max_len();
 
 void launch_prep_nodes(const int* offsets, int B, const float* X, const uint8_t* mask, int N, int* pstart, int* pend,
@@ -54,7 +54,7 @@ void launch_msg(int npt, bool dec, const float* hE, const int* E_idx, const floa
 void launch_edge_upd(int npt, float* hE, const int* E_idx, const float* P, const float* Q, const float* wstream,
                      const float* b12, const float* b13, const float* ln_g, const float* ln_b, int N,
                      cudaStream_t st);
-void launch_node_update(const NodeUpdArgs& a, cudaStream_t st);
+void launch_node_update(const NodeUpdArgs& a, int sms, cudaStream_t st);
 void launch_head(const HeadArgs& a, cudaStream_t st);
 
 }  // namespace tmpnn

@@ -88,19 +88,17 @@ inline std::vector<RawTensor> build_raw_table() {
 struct LayerNormW { int64_t g, b; };
 
 struct NodeUpdW {           // what node_update needs for one Enc/Dec layer
-    int64_t W3, b3;         // KN [128][128]
+    int64_t stream;         // KN chunks: W3 (4) | W_in column blocks 0..3 (4 each) | W_out (16) | projections (4 each)
+    int32_t nchunks;
+    int64_t b3, bin, bout;
     LayerNormW n1, n2;
-    int64_t Win, bin;       // KN [128][512]
-    int64_t Wout, bout;     // KN [512][128]
 };
 
 struct EncW {
     int64_t msg;            // [W1b | W2] KN, 8 chunks      (message kernel stream)
     int64_t b1, b2;
-    int64_t W1a, W1c;       // KN: h_V[i] / h_V[j] blocks of W1
     int64_t edge;           // [W11b | W12 | W13] KN, 12 chunks (edge-update stream)
     int64_t b11, b12, b13;
-    int64_t W11a, W11c;
     LayerNormW n3;
     NodeUpdW nu;
 };
@@ -108,7 +106,6 @@ struct EncW {
 struct DecW {
     int64_t msg;            // [W1b | W2] KN  (W1b = h_E block of the 512-wide W1)
     int64_t b1, b2;
-    int64_t W1a, W1d;       // h_V[i] block, h_V[j] block
     int64_t Tseq;           // [21][128] = W_s . W1c^T : the h_S[j] term folded per letter
     NodeUpdW nu;
 };
@@ -122,10 +119,8 @@ struct DevLayout {
     EncW enc[3];
     DecW dec[3];
     int64_t Ws;             // [21][128] embedding rows
-    int64_t la, la_b;       // KN [384][384], [384]
-    int64_t m1, m1_b;       // KN [384][64]
-    int64_t m2, m2_b;       // KN [64][32]
-    int64_t m3, m3_b;       // KN [32][21]
+    int64_t head;           // KN chunks: LA column blocks 0..2 (12 each) | both_out.1 (12) | .3 (2) | .5 (1), padded to 128 cols
+    int64_t la_b, m1_b, m2_b, m3_b;
     int64_t ddg;            // [2] = scale, shift
     int64_t zeros;          // [128] zeros (Q for the first encoder layer)
     int64_t total;

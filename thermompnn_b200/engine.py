@@ -107,11 +107,16 @@ class Engine:
         self._n_last = 0
 
     def close(self):
-        if getattr(self, "_ctx", None) is not None and self._ctx:
-            self._lib.tmpnn_destroy(self._ctx)
-            self._ctx = C.c_void_p()
+        ctx = getattr(self, "_ctx", None)
+        if ctx is not None and ctx.value:
+            self._ctx = None
+            self._lib.tmpnn_destroy(ctx)
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:   # interpreter shutdown
+            pass
 
     def _check(self, rc: int):
         if rc != 0:
