@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -72,7 +73,7 @@ struct tmpnn_ctx {
     bool stage_busy = false;
     // per-node
     DevBuf<int> pstart, pend;
-    DevBuf<float> atoms, maskf, hV, dec_prev, dec_last, Ssum, cnt, P, Q, P2, Q2, table;
+    DevBuf<float> atoms, maskf, hV, dec_prev, dec_last, Ssum, cnt, P, Q, P2, Q2, table, Spart;
     // per-edge
     DevBuf<int> E_idx;
     DevBuf<float> D_nb, hE;
@@ -80,6 +81,7 @@ struct tmpnn_ctx {
     int last_N = 0;
     float* last_table = nullptr;
     int debug_stop = 0;
+    bool use_tc = true;      // tensor-core edge kernels (TMPNN_TC=0 selects the FP32 SIMT generation, bring-up only)
 
     bool profiling = false;
     std::vector<ProfEntry> prof;
@@ -118,7 +120,7 @@ struct Prep {
     }
     int64_t alloc(int64_t n) {
         int64_t off = (int64_t)dev.size();
-        int64_t padded = (n + 31) / 32 * 32;   // keep every block 128-byte aligned
+        int64_t padded = (n + 255) / 256 * 256;   // keep every block 1024-byte aligned (bulk copies, swizzled images)
         dev.resize(dev.size() + padded, 0.f);
         return off;
     }
@@ -167,6 +169,29 @@ struct Prep {
         w.bout = vec(p + "dense.W_out.bias");
         return w;
     }
+    // Tensor-core image of W[:, col0:col0+128] (nn.Linear [out=128][in]): 4 K-chunks of ([128 n][32 k] hi | lo),
+    // rows 128 bytes, 16-byte chunks XOR-swizzled by (n & 7); hi/lo are the two tf32 words of the 3xTF32 split.
+    static float rna_tf32(float x) {
+        uint32_t u;
+        std::memcpy(&u, &x, 4);
+        u = (u + 0x1000u) & 0xffffe000u;
+        float r;
+        std::memcpy(&r, &u, 4);
+        return r;
+    }
+    void put_tc(int64_t off, const std::string& name, int col0) {
+        int out, in;
+        const float* W = find(name, &out, &in);
+        for (int c = 0; c < 4; ++c)
+            for (int n = 0; n < HID; ++n)
+                for (int kk = 0; kk < 32; ++kk) {
+                    const float x = W[(int64_t)n * in + col0 + c * 32 + kk];
+                    const float hi = rna_tf32(x), lo = rna_tf32(x - hi);
+                    const int64_t idx = off + (int64_t)c * 8192 + n * 32 + ((((kk >> 2) ^ (n & 7)) << 2) | (kk & 3));
+                    dev[idx] = hi;
+                    dev[idx + 4096] = lo;
+                }
+    }
     // KN of an nn.Linear [out][in] padded to 128 output columns, appended at off; returns floats written
     int64_t put_kn_padded(int64_t off, const std::string& name, int col0, int ncols_out_begin, int k_rows) {
         int out, in;
@@ -208,12 +233,19 @@ DevLayout prepare_weights(Prep& P) {
         e.msg = P.alloc(2 * HID * HID);
         P.put_kn(e.msg, p + "W1.weight", HID, HID);
         P.put_kn(e.msg + HID * HID, p + "W2.weight", 0, HID);
+        e.tc_msg = P.alloc(8 * 8192);
+        P.put_tc(e.tc_msg, p + "W1.weight", HID);
+        P.put_tc(e.tc_msg + 4 * 8192, p + "W2.weight", 0);
         e.b1 = P.vec(p + "W1.bias");
         e.b2 = P.vec(p + "W2.bias");
         e.edge = P.alloc(3 * HID * HID);
         P.put_kn(e.edge, p + "W11.weight", HID, HID);
         P.put_kn(e.edge + HID * HID, p + "W12.weight", 0, HID);
         P.put_kn(e.edge + 2 * HID * HID, p + "W13.weight", 0, HID);
+        e.tc_edge = P.alloc(12 * 8192);
+        P.put_tc(e.tc_edge, p + "W11.weight", HID);
+        P.put_tc(e.tc_edge + 4 * 8192, p + "W12.weight", 0);
+        P.put_tc(e.tc_edge + 8 * 8192, p + "W13.weight", 0);
         e.b11 = P.vec(p + "W11.bias");
         e.b12 = P.vec(p + "W12.bias");
         e.b13 = P.vec(p + "W13.bias");
@@ -239,6 +271,9 @@ DevLayout prepare_weights(Prep& P) {
         d.msg = P.alloc(2 * HID * HID);
         P.put_kn(d.msg, p + "W1.weight", HID, HID);
         P.put_kn(d.msg + HID * HID, p + "W2.weight", 0, HID);
+        d.tc_msg = P.alloc(8 * 8192);
+        P.put_tc(d.tc_msg, p + "W1.weight", HID);
+        P.put_tc(d.tc_msg + 4 * 8192, p + "W2.weight", 0);
         d.b1 = P.vec(p + "W1.bias");
         d.b2 = P.vec(p + "W2.bias");
         // h_S[j] term: W1[:, 256:384] . W_s[S_j]  -> one row per letter
@@ -422,6 +457,8 @@ int tmpnn_create(int device, tmpnn_ctx** out) {
         return bail(std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
     if ((e = kernels_init()) != cudaSuccess) return bail(std::string("kernels_init: ") + cudaGetErrorString(e));
     if ((e = node_kernels_init()) != cudaSuccess) return bail(std::string("node_kernels_init: ") + cudaGetErrorString(e));
+    if ((e = tc_kernels_init()) != cudaSuccess) return bail(std::string("tc_kernels_init: ") + cudaGetErrorString(e));
+    if (const char* env = std::getenv("TMPNN_TC")) ctx->use_tc = std::string(env) != "0";
     *out = ctx;
     return TMPNN_OK;
 }
@@ -439,6 +476,7 @@ void tmpnn_destroy(tmpnn_ctx* ctx) {
     ctx->pstart.release(); ctx->pend.release();
     ctx->atoms.release(); ctx->maskf.release(); ctx->hV.release(); ctx->dec_prev.release(); ctx->dec_last.release();
     ctx->Ssum.release(); ctx->cnt.release(); ctx->P.release(); ctx->Q.release(); ctx->P2.release(); ctx->Q2.release();
+    ctx->Spart.release();
     ctx->table.release(); ctx->E_idx.release(); ctx->D_nb.release(); ctx->hE.release();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -540,7 +578,7 @@ int tmpnn_run_batch(tmpnn_ctx* ctx, int32_t B, const int32_t* offsets, const flo
     CU(ctx->pstart.reserve(n)); CU(ctx->pend.reserve(n));
     CU(ctx->atoms.reserve(n * 16)); CU(ctx->maskf.reserve(n));
     CU(ctx->hV.reserve(n * HID)); CU(ctx->dec_prev.reserve(n * HID)); CU(ctx->dec_last.reserve(n * HID));
-    CU(ctx->Ssum.reserve(n * HID)); CU(ctx->cnt.reserve(n));
+    CU(ctx->Ssum.reserve(n * HID)); CU(ctx->cnt.reserve(n)); CU(ctx->Spart.reserve(n * 3 * HID));
     CU(ctx->P.reserve(n * HID)); CU(ctx->Q.reserve(n * HID)); CU(ctx->P2.reserve(n * HID)); CU(ctx->Q2.reserve(n * HID));
     CU(ctx->E_idx.reserve(ne)); CU(ctx->D_nb.reserve(ne)); CU(ctx->hE.reserve(ne * HID));
     float* d_table = out_table;
@@ -572,15 +610,23 @@ int tmpnn_run_batch(tmpnn_ctx* ctx, int32_t B, const int32_t* offsets, const flo
     if (!done && !stage_done(2)) {
         for (int l = 0; l < 3 && !done; ++l) {
             const EncW& e = L.enc[l];
-            { LaunchScope ls(ctx, st, "enc_msg");
-              if (l == 0)   // h_V = 0: P_i = b1, Q_j = 0
-                  launch_msg(npt, false, ctx->hE.p, ctx->E_idx.p, W + e.b1, 0, W + L.zeros, 0, ctx->maskf.p, W + e.msg,
-                             W + e.b2, ctx->Ssum.p, ctx->cnt.p, N, st);
-              else
-                  launch_msg(npt, false, ctx->hE.p, ctx->E_idx.p, ctx->P.p, HID, ctx->Q.p, HID, ctx->maskf.p, W + e.msg,
-                             W + e.b2, ctx->Ssum.p, ctx->cnt.p, N, st); }
+            {   // first layer: h_V = 0, so P_i = b1 and Q_j = 0 (one shared row each, stride 0)
+                const float* Pp = l == 0 ? W + e.b1 : ctx->P.p;
+                const float* Qp = l == 0 ? W + L.zeros : ctx->Q.p;
+                const int stride = l == 0 ? 0 : HID;
+                if (ctx->use_tc) {
+                    LaunchScope ls(ctx, st, "tc_enc_msg");
+                    launch_tc_msg(false, ctx->hE.p, ctx->E_idx.p, Pp, stride, Qp, stride, ctx->maskf.p, W + e.tc_msg, W + e.b2,
+                                  ctx->Spart.p, N, ctx->sm_count, st);
+                } else {
+                    LaunchScope ls(ctx, st, "enc_msg");
+                    launch_msg(npt, false, ctx->hE.p, ctx->E_idx.p, Pp, stride, Qp, stride, ctx->maskf.p, W + e.msg, W + e.b2,
+                               ctx->Ssum.p, ctx->cnt.p, N, st);
+                }
+            }
             NodeUpdArgs a{};
             a.weights = W; a.w = e.nu; a.Ssum = ctx->Ssum.p; a.cnt = ctx->cnt.p; a.hV = ctx->hV.p; a.hV_copy = nullptr;
+            a.Spart = ctx->use_tc ? ctx->Spart.p : nullptr; a.E_idx = ctx->E_idx.p; a.enc = 1;
             a.maskf = ctx->maskf.p; a.S = d_S; a.N = N;
             a.proj[0] = {e.b11, -1, ctx->P2.p};     // edge update of this layer
             a.proj[1] = {-1, -1, ctx->Q2.p};
@@ -595,20 +641,33 @@ int tmpnn_run_batch(tmpnn_ctx* ctx, int32_t B, const int32_t* offsets, const flo
             }
             a.nproj = 4;
             { LaunchScope ls(ctx, st, "node_update"); launch_node_update(a, ctx->sm_count, st); }
-            { LaunchScope ls(ctx, st, "edge_upd");
-              launch_edge_upd(npt, ctx->hE.p, ctx->E_idx.p, ctx->P2.p, ctx->Q2.p, W + e.edge, W + e.b12, W + e.b13,
-                              W + e.n3.g, W + e.n3.b, N, st); }
+            if (ctx->use_tc) {
+                LaunchScope ls(ctx, st, "tc_edge_upd");
+                launch_tc_edge_upd(ctx->hE.p, ctx->E_idx.p, ctx->P2.p, ctx->Q2.p, ctx->maskf.p, W + e.tc_edge, W + e.b12, W + e.b13,
+                                   W + e.n3.g, W + e.n3.b, N, ctx->sm_count, st);
+            } else {
+                LaunchScope ls(ctx, st, "edge_upd");
+                launch_edge_upd(npt, ctx->hE.p, ctx->E_idx.p, ctx->P2.p, ctx->Q2.p, W + e.edge, W + e.b12, W + e.b13,
+                                W + e.n3.g, W + e.n3.b, N, st);
+            }
             stage_done(3 + l);
         }
     }
     if (!done) {
         for (int l = 0; l < 3 && !done; ++l) {
             const DecW& d = L.dec[l];
-            { LaunchScope ls(ctx, st, "dec_msg");
-              launch_msg(npt, true, ctx->hE.p, ctx->E_idx.p, ctx->P.p, HID, ctx->Q.p, HID, ctx->maskf.p, W + d.msg,
-                         W + d.b2, ctx->Ssum.p, ctx->cnt.p, N, st); }
+            if (ctx->use_tc) {
+                LaunchScope ls(ctx, st, "tc_dec_msg");
+                launch_tc_msg(true, ctx->hE.p, ctx->E_idx.p, ctx->P.p, HID, ctx->Q.p, HID, ctx->maskf.p, W + d.tc_msg, W + d.b2,
+                              ctx->Spart.p, N, ctx->sm_count, st);
+            } else {
+                LaunchScope ls(ctx, st, "dec_msg");
+                launch_msg(npt, true, ctx->hE.p, ctx->E_idx.p, ctx->P.p, HID, ctx->Q.p, HID, ctx->maskf.p, W + d.msg,
+                           W + d.b2, ctx->Ssum.p, ctx->cnt.p, N, st);
+            }
             NodeUpdArgs a{};
             a.weights = W; a.w = d.nu; a.Ssum = ctx->Ssum.p; a.cnt = ctx->cnt.p; a.hV = ctx->hV.p;
+            a.Spart = ctx->use_tc ? ctx->Spart.p : nullptr; a.E_idx = ctx->E_idx.p; a.enc = 0;
             a.hV_copy = (l == 1) ? ctx->dec_prev.p : (l == 2 ? ctx->dec_last.p : nullptr);
             a.maskf = ctx->maskf.p; a.S = d_S; a.N = N;
             a.nproj = 0;
@@ -674,7 +733,11 @@ int tmpnn_set_profiling(tmpnn_ctx* ctx, int enabled) {
     return TMPNN_OK;
 }
 
-int tmpnn_profile_count(tmpnn_ctx* ctx) { return ctx ? (int)ctx->prof.size() : TMPNN_E_INVALID; }
+int tmpnn_profile_count(tmpnn_ctx* ctx) {
+    if (!ctx) return TMPNN_E_INVALID;
+    drain_profile(ctx);   // blocks until the recorded events have completed
+    return (int)ctx->prof.size();
+}
 
 int tmpnn_profile_get(tmpnn_ctx* ctx, int index, const char** kernel_name, double* total_ms, int64_t* launches) {
     if (!ctx || index < 0 || index >= (int)ctx->prof.size()) return TMPNN_E_INVALID;

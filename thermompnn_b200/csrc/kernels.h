@@ -16,8 +16,11 @@ struct ProjSpec {      // out[i] = h_V[i] . W (+ bias) (+ table[S_i]); W is the 
 struct NodeUpdArgs {
     const float* weights;
     NodeUpdW w;
-    const float* Ssum;   // [N][128] masked neighbour sum of the second GELU
+    const float* Ssum;   // [N][128] masked neighbour sum of the second GELU (SIMT message kernel), or
     const float* cnt;    // [N] sum of edge weights
+    const float* Spart;  // [N][3][128] per-32-row-block partial sums (tensor-core message kernel); then cnt is derived
+    const int* E_idx;    //   from E_idx / maskf here
+    int enc;             //   1: edge weight m_i m_j (encoder)   0: weight 1 (decoder)
     float* hV;           // [N][128] in/out
     float* hV_copy;      // optional second destination (decoder states kept for the head)
     const float* maskf;  // [N]
@@ -39,6 +42,7 @@ struct HeadArgs {
 
 cudaError_t kernels_init();
 cudaError_t node_kernels_init();
+cudaError_t tc_kernels_init();
 int knn_max_len();
 
 void launch_prep_nodes(const int* offsets, int B, const float* X, const uint8_t* mask, int N, int* pstart, int* pend,
@@ -54,6 +58,10 @@ void launch_msg(int npt, bool dec, const float* hE, const int* E_idx, const floa
 void launch_edge_upd(int npt, float* hE, const int* E_idx, const float* P, const float* Q, const float* wstream,
                      const float* b12, const float* b13, const float* ln_g, const float* ln_b, int N,
                      cudaStream_t st);
+void launch_tc_edge_upd(float* hE, const int* E_idx, const float* P, const float* Q, const float* maskf, const float* wimg,
+                        const float* b12, const float* b13, const float* ln_g, const float* ln_b, int N, int sms, cudaStream_t st);
+void launch_tc_msg(bool dec, const float* hE, const int* E_idx, const float* P, int p_stride, const float* Q, int q_stride,
+                   const float* maskf, const float* wimg, const float* b2, float* Spart, int N, int sms, cudaStream_t st);
 void launch_node_update(const NodeUpdArgs& a, int sms, cudaStream_t st);
 void launch_head(const HeadArgs& a, cudaStream_t st);
 

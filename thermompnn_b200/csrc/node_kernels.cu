@@ -133,9 +133,40 @@ __global__ void __launch_bounds__(NK_THREADS, 1) node_update_kernel(NodeUpdArgs 
     const float* wb = a.weights;
     NodeStream ws;
     ws.start(wb + a.w.stream, ring, a.w.nchunks);
-    for (int i = threadIdx.x; i < NT * HID; i += NK_THREADS) {
-        int node = node0 + i / HID;
-        x[i] = node < a.N ? a.Ssum[(size_t)node0 * HID + i] : 0.f;
+    float* cnt_s = red + 16 * NJ;                      // [NT]
+    if (a.Spart) {
+        // neighbour sum = the 2 or 3 per-block partials of the residue, added in block order; weight count from E_idx
+        for (int i = threadIdx.x; i < NT * HID; i += NK_THREADS) {
+            const int node = node0 + i / HID, c = i % HID;
+            float s = 0.f;
+            if (node < a.N) {
+                const int nparts = (node * KNB + KNB - 1) / 32 - (node * KNB) / 32 + 1;
+                const float* sp = a.Spart + (size_t)node * 3 * HID + c;
+                s = sp[0] + sp[HID];
+                if (nparts == 3) s += sp[2 * HID];
+            }
+            x[i] = s;
+        }
+        if (threadIdx.x < NT * 32) {                   // one warp per residue
+            const int t = threadIdx.x >> 5, lane = threadIdx.x & 31, node = node0 + t;
+            float c = 0.f;
+            if (node < a.N) {
+                const float mi = a.maskf[node];
+                for (int k = lane; k < KNB; k += 32) {
+                    const int j = a.E_idx[(size_t)node * KNB + k];
+                    if (j >= 0) c += a.enc ? mi * a.maskf[j] : 1.0f;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if (lane == 0) cnt_s[t] = c;
+        }
+    } else {
+        for (int i = threadIdx.x; i < NT * HID; i += NK_THREADS) {
+            int node = node0 + i / HID;
+            x[i] = node < a.N ? a.Ssum[(size_t)node0 * HID + i] : 0.f;
+        }
+        if (threadIdx.x < NT) cnt_s[threadIdx.x] = (node0 + threadIdx.x < a.N) ? a.cnt[node0 + threadIdx.x] : 0.f;
     }
     int g = 0;
     float res[NJ], h[NJ];
@@ -145,7 +176,7 @@ __global__ void __launch_bounds__(NK_THREADS, 1) node_update_kernel(NodeUpdArgs 
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
             int node = node0 + kq + 4 * j;
-            float c = node < a.N ? a.cnt[node] : 0.f;
+            float c = cnt_s[kq + 4 * j];
             float hv = node < a.N ? a.hV[(size_t)node * HID + n] : 0.f;
             h[j] = hv + fmaf(c, b3, res[j]) / MSG_SCALE;
         }
@@ -252,7 +283,7 @@ __global__ void __launch_bounds__(NK_THREADS, 1) head_kernel(HeadArgs a) {
 }
 
 template <int NT> static size_t smem_node_update() {
-    return sizeof(float) * (NK_RING * WCHUNK_FLOATS + NT * HID + NT * 4 * HID + 4 * NT * HID + 16 * (NT / 4));
+    return sizeof(float) * (NK_RING * WCHUNK_FLOATS + NT * HID + NT * 4 * HID + 4 * NT * HID + 16 * (NT / 4) + NT);
 }
 template <int NT> static size_t smem_head() {
     return sizeof(float) * (NK_RING * WCHUNK_FLOATS + 2 * NT * 3 * HID + 4 * NT * HID);

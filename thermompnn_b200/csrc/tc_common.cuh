@@ -1,0 +1,134 @@
+// Blackwell (sm_100a) primitives used by the tensor-core edge kernels: mbarrier, bulk async copy,
+// TMEM allocation, tcgen05.mma (kind::tf32, A from TMEM, B from shared memory), tcgen05.ld/st.
+//
+// Operand conventions (validated by csrc/tests/tc_gemm_test.cu on hardware):
+//   D[m][n] (fp32 accumulator): TMEM lane m, column d_col + n                    (M = 128 rows = 128 lanes)
+//   A[m][k] (tf32, from TMEM) : TMEM lane m, column a_col + k
+//   B[n][k] (tf32, from smem) : "K-major" = nn.Linear's own [out][in] order, stored as 128-byte-swizzled slabs:
+//       slab kb holds k in [32kb, 32kb+32): row n at byte n*128, 16-byte chunk c at ((c ^ (n & 7)) * 16)
+//       (slabs are 1024-byte aligned; 8-row groups are 1024 bytes apart = the descriptor's SBO)
+//   3xTF32: x = hi + lo with hi = x & 0xffffe000 (what the tensor core reads of x anyway) and lo = x - hi (exact);
+//       D = A_hi.B_hi + A_lo.B_hi + A_hi.B_lo, fp32 accumulation.  Dropped: lo.lo (<= 2^-20 relative).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tmpnn {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded spin: a protocol bug must not hang the GPU (a hung box is a strike); on timeout, trap.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+        if (spins > (1u << 26)) { asm volatile("trap;"); }
+    }
+}
+
+// ---- bulk async copy global -> shared, completion on an mbarrier ---------------------------------------------------
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---- TMEM -------------------------------------------------------------------------------------------------------
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {   // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "n"(NCOLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {        // the same warp that allocated
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// 32 lanes x 32 columns: thread t of the warp <-> lane (32*(warp%4) + t), registers <-> consecutive columns.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+        "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+        "r"(r[31])
+        : "memory");
+}
+
+// ---- descriptors ----------------------------------------------------------------------------------------------------
+// Shared-memory matrix descriptor (sm_100 format): K-major operand, SWIZZLE_128B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4)      // start address, 16-byte units      bits [0,14)
+           | ((uint64_t)1 << 16)                         // leading byte offset (unused here) bits [16,30)
+           | ((uint64_t)(1024 >> 4) << 32)               // stride byte offset = 1024         bits [32,46)
+           | ((uint64_t)1 << 46)                         // descriptor version (Blackwell)    bits [46,48)
+           | ((uint64_t)2 << 61);                        // layout: SWIZZLE_128B              bits [61,64)
+}
+// Instruction descriptor: D fp32, A/B tf32, both K-major, M x N tile.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// D[tmem d] (+)= A[tmem a] . B[smem desc]^T, one K = 8 step; issued by ONE thread.
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Arrive on an mbarrier once every MMA issued so far by this thread has completed (implies fence::before_thread_sync).
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ uint32_t tf32_hi(float x) { return __float_as_uint(x) & 0xffffe000u; }
+__device__ __forceinline__ uint32_t tf32_lo(float x, uint32_t hi) { return __float_as_uint(x - __uint_as_float(hi)); }
+
+// byte offset of element (row n, column k) inside a [rows x 128] operand stored as four SW128 slabs of `rows` rows
+__host__ __device__ constexpr uint32_t sw128_offset(int rows, int n, int k) {
+    return (uint32_t)((k >> 5) * rows * 128 + n * 128 + ((((k & 31) >> 2) ^ (n & 7)) << 4) + ((k & 3) << 2));
+}
+
+}  // namespace tc
+}  // namespace tmpnn

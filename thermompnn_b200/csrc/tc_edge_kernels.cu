@@ -1,0 +1,433 @@
+// Tensor-core (tcgen05) generation of the per-edge kernels.
+//
+// One CTA works on tiles of 128 consecutive edge rows (rows of the [N*48][128] h_E array; tiles ignore residue
+// boundaries).  Warp roles:
+//   warps 0-3  epilogue: thread t of warp w owns edge row 32w+t = TMEM lane 32w+t.  It turns each accumulator
+//              chunk into the next GEMM's A operand (bias / gathered projections, GELU, hi/lo split, tcgen05.st)
+//   warp 4     lane 0 issues tcgen05.mma (kind::tf32, A from TMEM, B from shared memory), owns the TMEM allocation
+//   warp 5     lane 0 streams weight chunks (pre-split, pre-swizzled 32 KB images) through a 3-slot ring (bulk copy)
+//   warp 6     gathers activations with cp.async: the h_E tile, the P rows and the neighbours' Q rows
+//
+// TMEM (512 columns): D0 | D1 | A_hi | A_lo, 128 columns each.  The accumulator is double buffered so that
+// stage l+1's MMAs (fed chunk by chunk as the epilogue of stage l produces A) run underneath that epilogue.
+// fp32 accuracy comes from the 3xTF32 split (tc_common.cuh).
+#include "common.cuh"
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace tmpnn {
+
+using namespace tc;
+
+namespace {
+
+constexpr int TC_ROWS = 128;
+constexpr int TC_THREADS = 224;
+constexpr int TC_WSLOTS = 3;
+constexpr uint32_t TC_WCHUNK_BYTES = 32768;   // [128 n][32 k] hi (16 KB) | lo (16 KB)
+constexpr uint32_t COL_D0 = 0, COL_D1 = 128, COL_AHI = 256, COL_ALO = 384;
+
+struct __align__(1024) TcSmem {
+    uint8_t wring[TC_WSLOTS][TC_WCHUNK_BYTES];   // 96 KB
+    float hE[4][TC_ROWS * 32];                   // 64 KB: four [128 rows][32 floats] slabs, 16-byte chunks XOR (row & 7)
+    float q[2][TC_ROWS * 32];                    // 32 KB: gathered Q rows, one 32-column chunk per buffer
+    float p[4][HID];                             // P rows of the (up to 4) residues the tile touches
+    float vec[4][HID];                           // per-kernel vectors (biases, LayerNorm gain/shift)
+    int jidx[TC_ROWS];
+    float wrow[TC_ROWS];                          // message weight of the row (0 for unused slots / rows past the end)
+    float mrow[TC_ROWS];                          // mask of the row's own residue
+    uint64_t w_full[TC_WSLOTS], w_empty[TC_WSLOTS];
+    uint64_t a_ready[4];                          // A chunk c written by all 128 epilogue threads
+    uint64_t d_ready[2];                          // accumulator buffer complete
+    uint64_t he_full, he_empty;
+    uint64_t q_full[2], q_empty[2];
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t rna_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+// x = hi + lo (+ <= 2^-22 |x|), both representable in tf32
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = rna_tf32(x);
+    lo = rna_tf32(x - __uint_as_float(hi));
+}
+
+// float offset of 16-byte chunk j (0..7) of row r inside a [128][32] swizzled slab
+__device__ __forceinline__ int slab_off(int r, int j) { return r * 32 + ((j ^ (r & 7)) << 2); }
+
+__device__ __forceinline__ void load_row_chunk(float (&v)[32], const float* slab, int r) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float4 t = *reinterpret_cast<const float4*>(slab + slab_off(r, j));
+        v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+    }
+}
+__device__ __forceinline__ void store_row_chunk(float* slab, int r, const float (&v)[32]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(slab + slab_off(r, j)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+
+// Write 32 values as columns [32c, 32c+32) of the next A operand (hi and lo planes) and publish the chunk.
+__device__ __forceinline__ void publish_A_chunk(uint32_t lane_addr, int c, const float (&v)[32], uint64_t* a_ready) {
+    uint32_t hi[32], lo[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) split_tf32(v[j], hi[j], lo[j]);
+    tmem_st32(lane_addr + COL_AHI + c * 32, hi);
+    tmem_st32(lane_addr + COL_ALO + c * 32, lo);
+    tmem_wait_st();
+    tc_fence_before();
+    mbar_arrive(a_ready);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+// One kernel, three kinds (same pipeline, different epilogues):
+//   UPD  h_E <- LN3(h_E + W13 gelu(W12 gelu(W11b.h_E + P_i + Q_j) + b12) + b13)       protein_mpnn_utils.py:834-838
+//        weight image W11b | W12 | W13
+//   ENC  g = gelu(W2 gelu(W1b.h_E + P_i + Q_j) + b2); per-residue sums of m_i m_j g     :819-825   image W1b | W2
+//   DEC  g = gelu(W2 gelu(P_i + m_i (W1b.h_E + R_j)) + b2); per-residue sums of g       :863-870, 1268-1272
+// ENC/DEC write, for every 32-row block of the edge array, the column sums of the rows belonging to each residue
+// into Spart[residue][block - first block of the residue][128]; node_update adds the (2 or 3) parts in a fixed
+// order, so the neighbour sum is deterministic.  W3 is applied there, after the sum.
+// ---------------------------------------------------------------------------------------------------------
+enum TcKind { TC_UPD = 0, TC_ENC = 1, TC_DEC = 2 };
+
+struct TcArgs {
+    float* hE;              // [N*48][128]; UPD updates it in place
+    const int* E_idx;       // [N*48]
+    const float* P; int p_stride;   // per-residue projection of h_V[i] (+bias); stride 0 = one shared row
+    const float* Q; int q_stride;   // per-residue projection of h_V[j] (R_j for DEC)
+    const float* maskf;     // [N]
+    const uint8_t* wimg;    // weight image
+    const float* v0;        // UPD: b12   ENC/DEC: b2
+    const float* v1;        // UPD: b13
+    const float* v2;        // UPD: LN gain
+    const float* v3;        // UPD: LN shift
+    float* Spart;           // ENC/DEC: [N][3][128]
+    int N, num_tiles;
+};
+
+// column sums over the 32 rows of a warp: on return lane l holds sum_rows v_row[l] in v[0]
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int s = 16, cnt = 16; s >= 1; s >>= 1, cnt >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < cnt; ++i) {
+            const float send = up ? v[i] : v[i + cnt];
+            const float keep = up ? v[i + cnt] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    return v[0];
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_kernel(TcArgs a) {
+    constexpr int STAGES = (KIND == TC_UPD) ? 3 : 2;
+    constexpr int WCHUNKS = 4 * STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    TcSmem& S = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int N = a.N, num_tiles = a.num_tiles;
+    const int total_rows = N * KNB;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < TC_WSLOTS; ++i) { mbar_init(&S.w_full[i], 1); mbar_init(&S.w_empty[i], 1); }
+        for (int i = 0; i < 4; ++i) mbar_init(&S.a_ready[i], 128);
+        for (int i = 0; i < 2; ++i) { mbar_init(&S.d_ready[i], 1); mbar_init(&S.q_full[i], 32); mbar_init(&S.q_empty[i], 128); }
+        mbar_init(&S.he_full, 64);
+        mbar_init(&S.he_empty, 128);
+        fence_barrier_init();
+    }
+    for (int i = threadIdx.x; i < HID; i += TC_THREADS) {
+        S.vec[0][i] = a.v0[i];
+        if (KIND == TC_UPD) { S.vec[1][i] = a.v1[i]; S.vec[2][i] = a.v2[i]; S.vec[3][i] = a.v3[i]; }
+    }
+    if (warp == 4) tmem_alloc<512>(&S.tmem_base);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = S.tmem_base;
+
+    if (warp == 5) {
+        // ---------------- weight producer ----------------
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+                for (int c = 0; c < WCHUNKS; ++c, ++it) {
+                    const uint32_t slot = it % TC_WSLOTS, use = it / TC_WSLOTS;
+                    if (use > 0) mbar_wait(&S.w_empty[slot], (use - 1) & 1);
+                    mbar_arrive_expect_tx(&S.w_full[slot], TC_WCHUNK_BYTES);
+                    bulk_g2s(S.wring[slot], a.wimg + (size_t)c * TC_WCHUNK_BYTES, TC_WCHUNK_BYTES, &S.w_full[slot]);
+                }
+        }
+    } else if (warp == 4) {
+        // ---------------- MMA issuer ----------------
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(128, 128);
+            uint32_t it = 0, g = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+                for (int l = 0; l < STAGES; ++l, ++g) {
+                    const uint32_t d = tmem + ((g & 1) ? COL_D1 : COL_D0);
+                    for (int c = 0; c < 4; ++c, ++it) {
+                        const uint32_t slot = it % TC_WSLOTS;
+                        mbar_wait(&S.a_ready[c], g & 1);
+                        mbar_wait(&S.w_full[slot], (it / TC_WSLOTS) & 1);
+                        tc_fence_after();
+                        const uint32_t wb = smem_u32(S.wring[slot]);
+#pragma unroll
+                        for (int s = 0; s < 4; ++s) {
+                            const uint32_t koff = c * 32 + s * 8;
+                            const uint64_t bh = make_desc_sw128(wb + s * 32), bl = make_desc_sw128(wb + 16384 + s * 32);
+                            mma_tf32_ts(d, tmem + COL_AHI + koff, bh, idesc, (c | s) != 0);
+                            mma_tf32_ts(d, tmem + COL_ALO + koff, bh, idesc, 1);
+                            mma_tf32_ts(d, tmem + COL_AHI + koff, bl, idesc, 1);
+                        }
+                        mma_commit(&S.w_empty[slot]);
+                        if (c == 3) mma_commit(&S.d_ready[g & 1]);
+                    }
+                }
+        }
+    } else if (warp == 6) {
+        // ---------------- activation producer ----------------
+        uint32_t ti = 0, qit = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+            const int row0 = tile * TC_ROWS;
+            const int node_lo = row0 / KNB;
+            if (ti > 0) mbar_wait(&S.he_empty, (ti - 1) & 1);
+            for (int r = 0; r < TC_ROWS; ++r) {          // one row per iteration, lane = 16-byte chunk
+                float* dst = &S.hE[lane >> 3][slab_off(r, lane & 7)];
+                if (row0 + r < total_rows) cp_async16(dst, a.hE + (size_t)(row0 + r) * HID + lane * 4);
+                else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                int node = node_lo + i; node = node < N ? node : N - 1;
+                cp_async16(&S.p[i][lane * 4], a.P + (size_t)node * a.p_stride + lane * 4);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = lane + 32 * i, row = row0 + r;
+                int j = N - 1;
+                float w = 0.f, mi = 0.f;
+                if (row < total_rows) {
+                    const int node = row / KNB;
+                    mi = a.maskf[node];
+                    j = a.E_idx[row];
+                    if (j < 0) j = node;                                   // unused slot: a finite dummy
+                    else w = (KIND == TC_ENC) ? mi * a.maskf[j] : 1.0f;    // mask_attend (protein_mpnn_utils.py:1232-1233)
+                }
+                S.jidx[r] = j; S.wrow[r] = w; S.mrow[r] = mi;
+            }
+            cp_async_arrive_noinc(&S.he_full);
+            mbar_arrive(&S.he_full);
+            __syncwarp();
+            for (int c = 0; c < 4; ++c, ++qit) {
+                const uint32_t b = qit & 1, use = qit >> 1;
+                if (use > 0) mbar_wait(&S.q_empty[b], (use - 1) & 1);
+                for (int i = 0; i < 32; ++i) {           // 4 rows per iteration, 8 lanes per row
+                    const int r = i * 4 + (lane >> 3), ch = lane & 7;
+                    cp_async16(&S.q[b][slab_off(r, ch)], a.Q + (size_t)S.jidx[r] * a.q_stride + c * 32 + ch * 4);
+                }
+                cp_async_arrive_noinc(&S.q_full[b]);
+            }
+        }
+        cp_async_wait<0>();
+    } else {
+        // ---------------- epilogue: thread <-> edge row ----------------
+        const int r = threadIdx.x;                        // 0..127
+        const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+        uint32_t ti = 0, g = 0, qit = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+            const int row0 = tile * TC_ROWS;
+            const int row = row0 + r;
+            int node_l = row / KNB - row0 / KNB;
+            node_l = node_l > 3 ? 3 : node_l;
+            // ---- input: h_E rows -> A
+            mbar_wait(&S.he_full, ti & 1);
+            const float w_r = S.wrow[r], m_i = S.mrow[r];
+            for (int c = 0; c < 4; ++c) {
+                float v[32];
+                load_row_chunk(v, S.hE[c], r);
+                publish_A_chunk(lane_addr, c, v, &S.a_ready[c]);
+            }
+            if (KIND != TC_UPD) mbar_arrive(&S.he_empty);      // staging tile is free: the next one can stream in
+            // ---- stage 1: gathered projections, GELU
+            mbar_wait(&S.d_ready[g & 1], (g >> 1) & 1);
+            tc_fence_after();
+            {
+                const uint32_t dcol = (g & 1) ? COL_D1 : COL_D0;
+                for (int c = 0; c < 4; ++c, ++qit) {
+                    const uint32_t b = qit & 1;
+                    uint32_t acc[32];
+                    tmem_ld32(lane_addr + dcol + c * 32, acc);
+                    mbar_wait(&S.q_full[b], (qit >> 1) & 1);
+                    float qv[32], v[32];
+                    load_row_chunk(qv, S.q[b], r);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float pj = S.p[node_l][c * 32 + j];
+                        const float pre = (KIND == TC_DEC) ? fmaf(m_i, __uint_as_float(acc[j]) + qv[j], pj)
+                                                           : (__uint_as_float(acc[j]) + pj + qv[j]);
+                        v[j] = gelu_erf(pre);
+                    }
+                    mbar_arrive(&S.q_empty[b]);
+                    publish_A_chunk(lane_addr, c, v, &S.a_ready[c]);
+                }
+            }
+            ++g;
+            if (KIND == TC_UPD) {
+                // ---- stage 2: + b12, GELU
+                mbar_wait(&S.d_ready[g & 1], (g >> 1) & 1);
+                tc_fence_after();
+                {
+                    const uint32_t dcol = (g & 1) ? COL_D1 : COL_D0;
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t acc[32];
+                        tmem_ld32(lane_addr + dcol + c * 32, acc);
+                        tmem_wait_ld();
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(__uint_as_float(acc[j]) + S.vec[0][c * 32 + j]);
+                        publish_A_chunk(lane_addr, c, v, &S.a_ready[c]);
+                    }
+                }
+                ++g;
+                // ---- stage 3: + b13 + h_E (residual), LayerNorm over the row (thread-local), back into the staging tile
+                mbar_wait(&S.d_ready[g & 1], (g >> 1) & 1);
+                tc_fence_after();
+                {
+                    const uint32_t dcol = (g & 1) ? COL_D1 : COL_D0;
+                    float shift = 0.f, s1 = 0.f, s2 = 0.f;
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t acc[32];
+                        tmem_ld32(lane_addr + dcol + c * 32, acc);
+                        float old[32];
+                        load_row_chunk(old, S.hE[c], r);
+                        tmem_wait_ld();
+                        if (c == 0) shift = __uint_as_float(acc[0]) + S.vec[1][0] + old[0];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            float x = __uint_as_float(acc[j]) + S.vec[1][c * 32 + j] + old[j];
+                            acc[j] = __float_as_uint(x);
+                            float dlt = x - shift;
+                            s1 += dlt;
+                            s2 = fmaf(dlt, dlt, s2);
+                        }
+                        tmem_st32(lane_addr + dcol + c * 32, acc);
+                    }
+                    tmem_wait_st();
+                    const float ms = s1 * (1.0f / HID);
+                    const float mean = shift + ms;
+                    const float var = fmaxf(s2 * (1.0f / HID) - ms * ms, 0.f);
+                    const float rstd = 1.0f / sqrtf(var + LN_EPS);
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t xv[32];
+                        tmem_ld32(lane_addr + dcol + c * 32, xv);
+                        tmem_wait_ld();
+                        float o[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            o[j] = (__uint_as_float(xv[j]) - mean) * rstd * S.vec[2][c * 32 + j] + S.vec[3][c * 32 + j];
+                        store_row_chunk(S.hE[c], r, o);
+                    }
+                }
+                ++g;
+                tc_fence_before();
+                epi_bar_sync();
+                // coalesced write-back of the tile: 4096 16-byte chunks
+                for (int i = 0; i < 32; ++i) {
+                    const int idx = i * 128 + r, rr = idx >> 5, ch = idx & 31;
+                    if (row0 + rr < total_rows) {
+                        float4 t = *reinterpret_cast<const float4*>(&S.hE[ch >> 3][slab_off(rr, ch & 7)]);
+                        *reinterpret_cast<float4*>(a.hE + (size_t)(row0 + rr) * HID + ch * 4) = t;
+                    }
+                }
+                mbar_arrive(&S.he_empty);
+            } else {
+                // ---- stage 2 (final): + b2, GELU, weight, per-residue column sums of this warp's 32 rows
+                mbar_wait(&S.d_ready[g & 1], (g >> 1) & 1);
+                tc_fence_after();
+                {
+                    const uint32_t dcol = (g & 1) ? COL_D1 : COL_D0;
+                    const int blk = tile * 4 + warp;                       // 32-row block of the edge array
+                    const int nA = (blk * 32) / KNB, nB = (blk * 32 + 31) / KNB;
+                    const bool inA = (row / KNB) == nA;
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t acc[32];
+                        tmem_ld32(lane_addr + dcol + c * 32, acc);
+                        tmem_wait_ld();
+                        float ga[32], gb[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float gl = gelu_erf(__uint_as_float(acc[j]) + S.vec[0][c * 32 + j]);
+                            const float wg = (w_r != 0.f) ? w_r * gl : 0.f;
+                            ga[j] = inA ? wg : 0.f;
+                            gb[j] = inA ? 0.f : wg;
+                        }
+                        const float sa = warp_colsum32(ga, lane);
+                        if (nA < N) a.Spart[((size_t)nA * 3 + (blk - (nA * KNB) / 32)) * HID + c * 32 + lane] = sa;
+                        if (nB != nA) {
+                            const float sb = warp_colsum32(gb, lane);
+                            if (nB < N) a.Spart[((size_t)nB * 3 + (blk - (nB * KNB) / 32)) * HID + c * 32 + lane] = sb;
+                        }
+                    }
+                }
+                ++g;
+            }
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc<512>(tmem);
+}
+
+cudaError_t tc_kernels_init() {
+    cudaError_t e;
+    const int bytes = (int)sizeof(TcSmem) + 1024;
+    if ((e = cudaFuncSetAttribute(tc_edge_kernel<TC_UPD>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(tc_edge_kernel<TC_ENC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(tc_edge_kernel<TC_DEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+static TcArgs tc_args(float* hE, const int* E_idx, const float* P, int p_stride, const float* Q, int q_stride, const float* maskf,
+                      const float* wimg, int N) {
+    TcArgs a{};
+    a.hE = hE; a.E_idx = E_idx; a.P = P; a.p_stride = p_stride; a.Q = Q; a.q_stride = q_stride; a.maskf = maskf;
+    a.wimg = reinterpret_cast<const uint8_t*>(wimg);
+    a.N = N;
+    a.num_tiles = (N * KNB + TC_ROWS - 1) / TC_ROWS;
+    return a;
+}
+
+void launch_tc_edge_upd(float* hE, const int* E_idx, const float* P, const float* Q, const float* maskf, const float* wimg,
+                        const float* b12, const float* b13, const float* ln_g, const float* ln_b, int N, int sms, cudaStream_t st) {
+    TcArgs a = tc_args(hE, E_idx, P, HID, Q, HID, maskf, wimg, N);
+    a.v0 = b12; a.v1 = b13; a.v2 = ln_g; a.v3 = ln_b;
+    const int grid = a.num_tiles < sms ? a.num_tiles : sms;
+    tc_edge_kernel<TC_UPD><<<grid, TC_THREADS, sizeof(TcSmem) + 1024, st>>>(a);
+}
+
+void launch_tc_msg(bool dec, const float* hE, const int* E_idx, const float* P, int p_stride, const float* Q, int q_stride,
+                   const float* maskf, const float* wimg, const float* b2, float* Spart, int N, int sms, cudaStream_t st) {
+    TcArgs a = tc_args(const_cast<float*>(hE), E_idx, P, p_stride, Q, q_stride, maskf, wimg, N);
+    a.v0 = b2; a.Spart = Spart;
+    const int grid = a.num_tiles < sms ? a.num_tiles : sms;
+    if (dec) tc_edge_kernel<TC_DEC><<<grid, TC_THREADS, sizeof(TcSmem) + 1024, st>>>(a);
+    else tc_edge_kernel<TC_ENC><<<grid, TC_THREADS, sizeof(TcSmem) + 1024, st>>>(a);
+}
+
+}  // namespace tmpnn

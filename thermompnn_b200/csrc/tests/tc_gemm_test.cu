@@ -1,0 +1,140 @@
+// Hardware check of the tcgen05 building blocks in tc_common.cuh: one 128x128x128 GEMM, A from TMEM
+// (written with tcgen05.st), B from pre-swizzled shared memory (bulk copy), 3xTF32 split, D read with tcgen05.ld.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tc_gemm_test tc_gemm_test.cu && ./tc_gemm_test
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "../tc_common.cuh"
+
+using namespace tmpnn::tc;
+
+constexpr int M = 128, N = 128, K = 128;
+constexpr uint32_t D_COL = 0, AHI_COL = 128, ALO_COL = 256;
+
+__global__ void __launch_bounds__(192) gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bimg /* hi | lo images */,
+                                                   float* __restrict__ Dout, int mode) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* b_hi = smem;              // 64 KB
+    uint8_t* b_lo = smem + 65536;      // 64 KB
+    __shared__ uint64_t bar_b, bar_a, bar_d;
+    __shared__ uint32_t tmem_base_s;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar_b, 1);
+        mbar_init(&bar_a, 128);
+        mbar_init(&bar_d, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc<512>(&tmem_base_s);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+
+    if (warp == 5 && lane == 0) {                       // producer: weights
+        mbar_arrive_expect_tx(&bar_b, 131072);
+        bulk_g2s(b_hi, Bimg, 65536, &bar_b);
+        bulk_g2s(b_lo, Bimg + 16384, 65536, &bar_b);
+    }
+    if (warp < 4) {                                     // A rows -> TMEM (hi, lo)
+        const int row = warp * 32 + lane;
+        const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+        for (int c = 0; c < 4; ++c) {
+            uint32_t hi[32], lo[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float x = A[row * K + c * 32 + j];
+                hi[j] = tf32_hi(x);
+                lo[j] = tf32_lo(x, hi[j]);
+            }
+            tmem_st32(lane_addr + AHI_COL + c * 32, hi);
+            tmem_st32(lane_addr + ALO_COL + c * 32, lo);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(&bar_a);
+    }
+    if (warp == 4 && lane == 0) {                       // MMA issuer
+        mbar_wait(&bar_b, 0);
+        mbar_wait(&bar_a, 0);
+        tc_fence_after();
+        const uint32_t idesc = make_idesc_tf32(M, N);
+        const uint32_t bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+        uint32_t acc = 0;
+        for (int kb = 0; kb < 4; ++kb)
+            for (int s = 0; s < 4; ++s) {
+                const uint32_t koff = kb * 32 + s * 8;
+                const uint64_t dh = make_desc_sw128(bh + kb * 16384 + s * 32), dl = make_desc_sw128(bl + kb * 16384 + s * 32);
+                mma_tf32_ts(tmem + D_COL, tmem + AHI_COL + koff, dh, idesc, acc);
+                acc = 1;
+                if (mode == 3) {
+                    mma_tf32_ts(tmem + D_COL, tmem + ALO_COL + koff, dh, idesc, 1);
+                    mma_tf32_ts(tmem + D_COL, tmem + AHI_COL + koff, dl, idesc, 1);
+                }
+            }
+        mma_commit(&bar_d);
+    }
+    if (warp < 4) {                                     // epilogue: D -> global
+        mbar_wait(&bar_d, 0);
+        tc_fence_after();
+        const int row = warp * 32 + lane;
+        const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+        for (int c = 0; c < 4; ++c) {
+            uint32_t v[32];
+            tmem_ld32(lane_addr + D_COL + c * 32, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) Dout[row * N + c * 32 + j] = __uint_as_float(v[j]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc<512>(tmem);
+}
+
+int main() {
+    std::vector<float> A(M * K), W(N * K), D(M * N), img(2 * N * K);
+    srand(1);
+    for (auto& x : A) x = 4.f * ((float)rand() / RAND_MAX - 0.5f);
+    for (auto& x : W) x = 0.5f * ((float)rand() / RAND_MAX - 0.5f);
+    for (int n = 0; n < N; ++n)
+        for (int k = 0; k < K; ++k) {
+            float x = W[n * K + k];
+            uint32_t u; memcpy(&u, &x, 4);
+            uint32_t h = u & 0xffffe000u;
+            float hf; memcpy(&hf, &h, 4);
+            float lf = x - hf;
+            uint32_t off = sw128_offset(N, n, k) / 4;
+            img[off] = hf;
+            img[N * K + off] = lf;
+        }
+    float *dA, *dB, *dD;
+    cudaMalloc(&dA, A.size() * 4); cudaMalloc(&dB, img.size() * 4); cudaMalloc(&dD, D.size() * 4);
+    cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dB, img.data(), img.size() * 4, cudaMemcpyHostToDevice);
+    cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072 + 1024);
+    int rc = 0;
+    for (int mode : {1, 3}) {
+        cudaMemset(dD, 0, D.size() * 4);
+        gemm_kernel<<<1, 192, 131072, 0>>>(dA, dB, dD, mode);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("mode %d: CUDA error %s\n", mode, cudaGetErrorString(e)); return 2; }
+        cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
+        double maxerr = 0, maxref = 0;
+        for (int m = 0; m < M; ++m)
+            for (int n = 0; n < N; ++n) {
+                double r = 0;
+                for (int k = 0; k < K; ++k) r += (double)A[m * K + k] * (double)W[n * K + k];
+                maxerr = fmax(maxerr, fabs(r - D[m * N + n]));
+                maxref = fmax(maxref, fabs(r));
+            }
+        printf("mode %d (%s): max |D - ref| = %.3e  (max |ref| = %.2f, rel %.2e)\n", mode, mode == 3 ? "3xTF32" : "1xTF32", maxerr, maxref,
+               maxerr / maxref);
+        if (mode == 3 && !(maxerr / maxref < 2e-6)) rc = 1;
+        if (mode == 1 && !(maxerr / maxref < 5e-3)) rc = 1;
+    }
+    printf(rc ? "FAIL\n" : "PASS\n");
+    return rc;
+}

@@ -96,8 +96,10 @@ struct NodeUpdW {           // what node_update needs for one Enc/Dec layer
 
 struct EncW {
     int64_t msg;            // [W1b | W2] KN, 8 chunks      (message kernel stream)
+    int64_t tc_msg;         // the same two matrices as tensor-core images (8 x 32 KB)
     int64_t b1, b2;
     int64_t edge;           // [W11b | W12 | W13] KN, 12 chunks (edge-update stream)
+    int64_t tc_edge;        // same three matrices as tensor-core images: 12 x ([128 n][32 k] hi | lo), 128B-swizzled
     int64_t b11, b12, b13;
     LayerNormW n3;
     NodeUpdW nu;
@@ -105,6 +107,7 @@ struct EncW {
 
 struct DecW {
     int64_t msg;            // [W1b | W2] KN  (W1b = h_E block of the 512-wide W1)
+    int64_t tc_msg;
     int64_t b1, b2;
     int64_t Tseq;           // [21][128] = W_s . W1c^T : the h_S[j] term folded per letter
     NodeUpdW nu;
