@@ -55,17 +55,18 @@ def test_layerwise(name, gpu_model):
         hE = eng.fetch("h_E")[:6, :K]
         same = (E_idx[:6, :K] == d["E_idx"][:6]) & valid[:6, None]   # gap rows pick arbitrary (all-tie) neighbours
         assert same[valid[:6]].mean() > 0.9
-        assert np.abs(hE - d["h_E0_head"])[same].max() <= 2e-5
+        # h_E reaches |32|; 3xTF32 tensor-core GEMMs are ~3e-6 relative (fp32 SIMT was 6e-7)
+        assert np.abs(hE - d["h_E0_head"])[same].max() <= 2e-4
         for l in range(3):
             eng.set_debug_stop(3 + l)
             eng.run(p.offsets, p.X, p.S, p.residue_idx, p.chain_enc, p.mask)
-            assert np.abs(eng.fetch("h_V") - d[f"enc{l}_h_V"]).max() <= 5e-5
+            assert np.abs(eng.fetch("h_V") - d[f"enc{l}_h_V"]).max() <= 1e-4
             hE = eng.fetch("h_E")[:6, :K]
-            assert np.abs(hE - d[f"enc{l}_h_E_head"])[same].max() <= 1e-4
+            assert np.abs(hE - d[f"enc{l}_h_E_head"])[same].max() <= 2e-4
         for l in range(3):
             eng.set_debug_stop(6 + l)
             eng.run(p.offsets, p.X, p.S, p.residue_idx, p.chain_enc, p.mask)
-            assert np.abs(eng.fetch("h_V") - d[f"dec{l}_h_V"]).max() <= 5e-5
+            assert np.abs(eng.fetch("h_V") - d[f"dec{l}_h_V"]).max() <= 1e-4
     finally:
         eng.set_debug_stop(0)
 

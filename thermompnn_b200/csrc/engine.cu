@@ -179,10 +179,10 @@ struct Prep {
         std::memcpy(&r, &u, 4);
         return r;
     }
-    void put_tc(int64_t off, const std::string& name, int col0) {
+    void put_tc(int64_t off, const std::string& name, int col0, int nchunks = 4) {
         int out, in;
         const float* W = find(name, &out, &in);
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < nchunks; ++c)
             for (int n = 0; n < HID; ++n)
                 for (int kk = 0; kk < 32; ++kk) {
                     const float x = W[(int64_t)n * in + col0 + c * 32 + kk];
@@ -218,6 +218,9 @@ DevLayout prepare_weights(Prep& P) {
     L.feat = P.alloc((int64_t)(EDGE_IN + HID) * HID);
     P.put_kn(L.feat, pm + "features.edge_embedding.weight", 0, EDGE_IN);
     P.put_kn(L.feat + (int64_t)EDGE_IN * HID, pm + "W_e.weight", 0, HID);
+    L.tc_feat = P.alloc(17 * 8192);
+    P.put_tc(L.tc_feat, pm + "features.edge_embedding.weight", 0, 13);
+    P.put_tc(L.tc_feat + 13 * 8192, pm + "W_e.weight", 0, 4);
     L.be = P.vec(pm + "W_e.bias");
     L.ne = P.ln(pm + "features.norm_edges");
     {   // torch.linspace(2., 22., 16) in fp32 (protein_mpnn_utils.py:1113-1114)
@@ -602,9 +605,15 @@ int tmpnn_run_batch(tmpnn_ctx* ctx, int32_t B, const int32_t* offsets, const flo
     { LaunchScope ls(ctx, st, "knn");
       launch_knn(ctx->atoms.p, ctx->maskf.p, ctx->pstart.p, ctx->pend.p, N, lmax, ctx->E_idx.p, ctx->D_nb.p, st); }
     if (!stage_done(1)) {
-        { LaunchScope ls(ctx, st, "edge_feat");
-          launch_edge_feat(npt, ctx->atoms.p, ctx->E_idx.p, ctx->D_nb.p, d_r, d_c, W + L.pos_table, W + L.rbf_mu,
-                           W + L.feat, W + L.ne.g, W + L.ne.b, W + L.be, ctx->hE.p, N, st); }
+        if (ctx->use_tc) {
+            LaunchScope ls(ctx, st, "tc_edge_feat");
+            launch_tc_edge_feat(ctx->atoms.p, ctx->E_idx.p, ctx->D_nb.p, d_r, d_c, W + L.pos_table, W + L.rbf_mu, W + L.tc_feat,
+                                W + L.ne.g, W + L.ne.b, W + L.be, ctx->hE.p, N, ctx->sm_count, st);
+        } else {
+            LaunchScope ls(ctx, st, "edge_feat");
+            launch_edge_feat(npt, ctx->atoms.p, ctx->E_idx.p, ctx->D_nb.p, d_r, d_c, W + L.pos_table, W + L.rbf_mu,
+                             W + L.feat, W + L.ne.g, W + L.ne.b, W + L.be, ctx->hE.p, N, st);
+        }
         CU(cudaMemsetAsync(ctx->hV.p, 0, n * HID * sizeof(float), st));
     }
     if (!done && !stage_done(2)) {

@@ -135,15 +135,13 @@ __global__ void __launch_bounds__(NK_THREADS, 1) node_update_kernel(NodeUpdArgs 
     ws.start(wb + a.w.stream, ring, a.w.nchunks);
     float* cnt_s = red + 16 * NJ;                      // [NT]
     if (a.Spart) {
-        // neighbour sum = the 2 or 3 per-block partials of the residue, added in block order; weight count from E_idx
+        // neighbour sum = the three 16-row partials of the residue, added in order; weight count from E_idx
         for (int i = threadIdx.x; i < NT * HID; i += NK_THREADS) {
             const int node = node0 + i / HID, c = i % HID;
             float s = 0.f;
             if (node < a.N) {
-                const int nparts = (node * KNB + KNB - 1) / 32 - (node * KNB) / 32 + 1;
                 const float* sp = a.Spart + (size_t)node * 3 * HID + c;
-                s = sp[0] + sp[HID];
-                if (nparts == 3) s += sp[2 * HID];
+                s = (sp[0] + sp[HID]) + sp[2 * HID];
             }
             x[i] = s;
         }

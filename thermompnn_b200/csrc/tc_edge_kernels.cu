@@ -96,9 +96,9 @@ __device__ __forceinline__ void publish_A_chunk(uint32_t lane_addr, int c, const
 //        weight image W11b | W12 | W13
 //   ENC  g = gelu(W2 gelu(W1b.h_E + P_i + Q_j) + b2); per-residue sums of m_i m_j g     :819-825   image W1b | W2
 //   DEC  g = gelu(W2 gelu(P_i + m_i (W1b.h_E + R_j)) + b2); per-residue sums of g       :863-870, 1268-1272
-// ENC/DEC write, for every 32-row block of the edge array, the column sums of the rows belonging to each residue
-// into Spart[residue][block - first block of the residue][128]; node_update adds the (2 or 3) parts in a fixed
-// order, so the neighbour sum is deterministic.  W3 is applied there, after the sum.
+// ENC/DEC write the column sums of every 16-row sub-block of the edge array (a residue is exactly three of them)
+// into Spart[residue][0..2][128]; node_update adds the three parts in order, so the neighbour sum is deterministic
+// and independent of where the residue sits in the batch.  W3 is applied there, after the sum.
 // ---------------------------------------------------------------------------------------------------------
 enum TcKind { TC_UPD = 0, TC_ENC = 1, TC_DEC = 2 };
 
@@ -117,10 +117,11 @@ struct TcArgs {
     int N, num_tiles;
 };
 
-// column sums over the 32 rows of a warp: on return lane l holds sum_rows v_row[l] in v[0]
-__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+// Column sums over each 16-row half of a warp (half-warps never straddle a residue: 48 = 3 x 16).
+// On return lane l holds, for its half, the sums of columns 2*(l&15) and 2*(l&15)+1 in v[0], v[1].
+__device__ __forceinline__ void halfwarp_colsum32(float (&v)[32], int lane) {
 #pragma unroll
-    for (int s = 16, cnt = 16; s >= 1; s >>= 1, cnt >>= 1) {
+    for (int s = 8, cnt = 16; s >= 1; s >>= 1, cnt >>= 1) {
         const bool up = (lane & s) != 0;
 #pragma unroll
         for (int i = 0; i < cnt; ++i) {
@@ -129,7 +130,6 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
             v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
         }
     }
-    return v[0];
 }
 
 template <int KIND>
@@ -362,31 +362,280 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_kernel(TcArgs a) {
                 tc_fence_after();
                 {
                     const uint32_t dcol = (g & 1) ? COL_D1 : COL_D0;
-                    const int blk = tile * 4 + warp;                       // 32-row block of the edge array
-                    const int nA = (blk * 32) / KNB, nB = (blk * 32 + 31) / KNB;
-                    const bool inA = (row / KNB) == nA;
+                    const int sb = (row0 + warp * 32) / 16 + (lane >> 4);   // 16-row sub-block of the edge array
+                    const int node = sb / 3, part = sb - node * 3;
                     for (int c = 0; c < 4; ++c) {
                         uint32_t acc[32];
                         tmem_ld32(lane_addr + dcol + c * 32, acc);
                         tmem_wait_ld();
-                        float ga[32], gb[32];
+                        float gv[32];
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const float gl = gelu_erf(__uint_as_float(acc[j]) + S.vec[0][c * 32 + j]);
-                            const float wg = (w_r != 0.f) ? w_r * gl : 0.f;
-                            ga[j] = inA ? wg : 0.f;
-                            gb[j] = inA ? 0.f : wg;
+                            gv[j] = (w_r != 0.f) ? w_r * gl : 0.f;
                         }
-                        const float sa = warp_colsum32(ga, lane);
-                        if (nA < N) a.Spart[((size_t)nA * 3 + (blk - (nA * KNB) / 32)) * HID + c * 32 + lane] = sa;
-                        if (nB != nA) {
-                            const float sb = warp_colsum32(gb, lane);
-                            if (nB < N) a.Spart[((size_t)nB * 3 + (blk - (nB * KNB) / 32)) * HID + c * 32 + lane] = sb;
-                        }
+                        halfwarp_colsum32(gv, lane);
+                        if (node < N)
+                            *reinterpret_cast<float2*>(a.Spart + ((size_t)node * 3 + part) * HID + c * 32 + 2 * (lane & 15)) =
+                                make_float2(gv[0], gv[1]);
                     }
                 }
                 ++g;
             }
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc<512>(tmem);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// edge_feat (tensor cores): per edge 16 positional + 25x16 RBF features (computed by the row's thread straight
+// into the A operand) -> edge_embedding (416 -> 128, 13 K-chunks through 4 recycled A slots) -> LayerNorm
+// (thread-local) -> W_e + b  => h_E          (protein_mpnn_utils.py:1111-1125, 1142-1179, 1229)
+// ---------------------------------------------------------------------------------------------------------
+__constant__ int8_t c_tc_pair_a[NPAIR] = {1, 0, 2, 3, 4, 1, 1, 1, 1, 0, 0, 0, 4, 4, 3, 0, 2, 3, 4, 2, 3, 4, 2, 3, 2};
+__constant__ int8_t c_tc_pair_b[NPAIR] = {1, 0, 2, 3, 4, 0, 2, 3, 4, 2, 3, 4, 2, 3, 2, 1, 1, 1, 1, 0, 0, 0, 4, 4, 3};
+
+struct __align__(1024) TcFeatSmem {
+    uint8_t wring[TC_WSLOTS][TC_WCHUNK_BYTES];   // 96 KB
+    float out[4][TC_ROWS * 32];                  // 64 KB output staging (same swizzled slabs as TcSmem::hE)
+    float ajT[16][TC_ROWS];                      // neighbour atoms, component-major: [3*atom + xyz][row]
+    float ai[4][16];                             // atoms of the (up to 4) residues the tile touches
+    float dnb[TC_ROWS];
+    int posq[TC_ROWS];
+    float pos_table[66 * 16];
+    float vec[3][HID];                           // LN gain, LN shift, W_e bias
+    float mu[16];
+    uint64_t w_full[TC_WSLOTS], w_empty[TC_WSLOTS];
+    uint64_t a_ready[4], a_free[4];
+    uint64_t d_ready[2];
+    uint64_t in_full, in_empty;
+    uint32_t tmem_base;
+};
+
+struct TcFeatArgs {
+    const float* atoms;       // [N][16]
+    const int* E_idx;         // [N*48]
+    const float* D_nb;        // [N*48]
+    const int* ridx;
+    const int* cenc;
+    const float* pos_table;   // [66][16]
+    const float* rbf_mu;      // [16]
+    const uint8_t* wimg;      // 13 + 4 chunks
+    const float* ln_g;
+    const float* ln_b;
+    const float* b_e;
+    float* hE;
+    int N, num_tiles;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_feat_kernel(TcFeatArgs a) {
+    constexpr int K1_CHUNKS = EDGE_IN / 32;   // 13
+    extern __shared__ uint8_t smem_raw[];
+    TcFeatSmem& S = *reinterpret_cast<TcFeatSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int N = a.N, num_tiles = a.num_tiles;
+    const int total_rows = N * KNB;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < TC_WSLOTS; ++i) { mbar_init(&S.w_full[i], 1); mbar_init(&S.w_empty[i], 1); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&S.a_ready[i], 128); mbar_init(&S.a_free[i], 1); }
+        for (int i = 0; i < 2; ++i) mbar_init(&S.d_ready[i], 1);
+        mbar_init(&S.in_full, 32);
+        mbar_init(&S.in_empty, 128);
+        fence_barrier_init();
+    }
+    for (int i = threadIdx.x; i < HID; i += TC_THREADS) { S.vec[0][i] = a.ln_g[i]; S.vec[1][i] = a.ln_b[i]; S.vec[2][i] = a.b_e[i]; }
+    for (int i = threadIdx.x; i < 66 * 16; i += TC_THREADS) S.pos_table[i] = a.pos_table[i];
+    if (threadIdx.x < 16) S.mu[threadIdx.x] = a.rbf_mu[threadIdx.x];
+    if (warp == 4) tmem_alloc<512>(&S.tmem_base);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = S.tmem_base;
+
+    if (warp == 5) {
+        if (lane == 0) {                                  // weight producer
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+                for (int c = 0; c < K1_CHUNKS + 4; ++c, ++it) {
+                    const uint32_t slot = it % TC_WSLOTS, use = it / TC_WSLOTS;
+                    if (use > 0) mbar_wait(&S.w_empty[slot], (use - 1) & 1);
+                    mbar_arrive_expect_tx(&S.w_full[slot], TC_WCHUNK_BYTES);
+                    bulk_g2s(S.wring[slot], a.wimg + (size_t)c * TC_WCHUNK_BYTES, TC_WCHUNK_BYTES, &S.w_full[slot]);
+                }
+        }
+    } else if (warp == 4) {
+        if (lane == 0) {                                  // MMA issuer
+            const uint32_t idesc = make_idesc_tf32(128, 128);
+            uint32_t it = 0, g = 0, acnt[4] = {0, 0, 0, 0};
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+                for (int l = 0; l < 2; ++l, ++g) {
+                    const uint32_t d = tmem + ((g & 1) ? COL_D1 : COL_D0);
+                    const int nch = l == 0 ? K1_CHUNKS : 4;
+                    for (int c = 0; c < nch; ++c, ++it) {
+                        const uint32_t slot = it % TC_WSLOTS, as = c & 3;
+                        mbar_wait(&S.a_ready[as], acnt[as] & 1);
+                        ++acnt[as];
+                        mbar_wait(&S.w_full[slot], (it / TC_WSLOTS) & 1);
+                        tc_fence_after();
+                        const uint32_t wb = smem_u32(S.wring[slot]);
+#pragma unroll
+                        for (int s = 0; s < 4; ++s) {
+                            const uint32_t koff = as * 32 + s * 8;
+                            const uint64_t bh = make_desc_sw128(wb + s * 32), bl = make_desc_sw128(wb + 16384 + s * 32);
+                            mma_tf32_ts(d, tmem + COL_AHI + koff, bh, idesc, (c | s) != 0);
+                            mma_tf32_ts(d, tmem + COL_ALO + koff, bh, idesc, 1);
+                            mma_tf32_ts(d, tmem + COL_AHI + koff, bl, idesc, 1);
+                        }
+                        mma_commit(&S.w_empty[slot]);
+                        mma_commit(&S.a_free[as]);
+                        if (c == nch - 1) mma_commit(&S.d_ready[g & 1]);
+                    }
+                }
+        }
+    } else if (warp == 6) {
+        uint32_t ti = 0;                                  // per-row inputs
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+            const int row0 = tile * TC_ROWS;
+            const int node_lo = row0 / KNB;
+            if (ti > 0) mbar_wait(&S.in_empty, (ti - 1) & 1);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = lane + 32 * i, row = row0 + r;
+                int self = row / KNB; self = self < N ? self : N - 1;
+                int j = -1;
+                float dn = 0.f;
+                if (row < total_rows) { j = a.E_idx[row]; if (j >= 0) dn = a.D_nb[row]; }
+                if (j < 0) j = self;                       // unused slot: a well-defined dummy edge, never read downstream
+                S.dnb[r] = dn;
+                int q = a.ridx[self] - a.ridx[j] + 32;
+                q = q < 0 ? 0 : (q > 64 ? 64 : q);
+                S.posq[r] = (a.cenc[self] == a.cenc[j]) ? q : 65;          // PositionalEncodings, protein_mpnn_utils.py:904-905
+                const float4* src = reinterpret_cast<const float4*>(a.atoms + (size_t)j * 16);
+                const float4 a0 = __ldg(src), a1 = __ldg(src + 1), a2 = __ldg(src + 2), a3 = __ldg(src + 3);
+                const float v[16] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w, a3.x, a3.y, a3.z, a3.w};
+#pragma unroll
+                for (int k = 0; k < 16; ++k) S.ajT[k][r] = v[k];
+            }
+            if (lane < 4) {
+                int node = node_lo + lane; node = node < N ? node : N - 1;
+                const float4* src = reinterpret_cast<const float4*>(a.atoms + (size_t)node * 16);
+                float4* dst = reinterpret_cast<float4*>(S.ai[lane]);
+                dst[0] = __ldg(src); dst[1] = __ldg(src + 1); dst[2] = __ldg(src + 2); dst[3] = __ldg(src + 3);
+            }
+            mbar_arrive(&S.in_full);
+        }
+    } else {
+        const int r = threadIdx.x;
+        const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+        uint32_t ti = 0, g = 0, pub[4] = {0, 0, 0, 0};
+        auto publish = [&](int slot, const float (&v)[32]) {
+            if (pub[slot] > 0) mbar_wait(&S.a_free[slot], (pub[slot] - 1) & 1);   // the MMAs that read this slot are done
+            ++pub[slot];
+            tc_fence_after();
+            publish_A_chunk(lane_addr, slot, v, &S.a_ready[slot]);
+        };
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+            const int row0 = tile * TC_ROWS;
+            const int row = row0 + r;
+            int node_l = row / KNB - row0 / KNB;
+            node_l = node_l > 3 ? 3 : node_l;
+            mbar_wait(&S.in_full, ti & 1);
+            // ---- features -> A, 32 columns at a time
+            for (int c = 0; c < K1_CHUNKS; ++c) {
+                float v[32];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (c == 0 && h == 0) {
+                        const float* pt = &S.pos_table[S.posq[r] * 16];
+#pragma unroll
+                        for (int t = 0; t < 16; ++t) v[t] = pt[t];
+                    } else {
+                        const int p = (c == 0) ? 0 : 2 * c - 1 + h;
+                        float D;
+                        if (p == 0) {
+                            D = S.dnb[r];                  // the masked top-k distance itself (protein_mpnn_utils.py:1142)
+                        } else {
+                            const int ia = 3 * c_tc_pair_a[p], ib = 3 * c_tc_pair_b[p];
+                            const float dx = __fsub_rn(S.ai[node_l][ia], S.ajT[ib][r]);
+                            const float dy = __fsub_rn(S.ai[node_l][ia + 1], S.ajT[ib + 1][r]);
+                            const float dz = __fsub_rn(S.ai[node_l][ia + 2], S.ajT[ib + 2][r]);
+                            const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                            D = __fsqrt_rn(__fadd_rn(d2, 1e-6f));
+                        }
+#pragma unroll
+                        for (int t = 0; t < 16; ++t) {
+                            const float z = (D - S.mu[t]) * 0.8f;          // / sigma, sigma = 1.25
+                            v[h * 16 + t] = __expf(-(z * z));
+                        }
+                    }
+                }
+                publish(c & 3, v);
+            }
+            mbar_arrive(&S.in_empty);
+            // ---- norm_edges (thread-local LayerNorm over the 128 accumulator columns) -> A of the W_e GEMM
+            mbar_wait(&S.d_ready[g & 1], (g >> 1) & 1);
+            tc_fence_after();
+            {
+                const uint32_t dcol = (g & 1) ? COL_D1 : COL_D0;
+                float shift = 0.f, s1 = 0.f, s2 = 0.f;
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t acc[32];
+                    tmem_ld32(lane_addr + dcol + c * 32, acc);
+                    tmem_wait_ld();
+                    if (c == 0) shift = __uint_as_float(acc[0]);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float dlt = __uint_as_float(acc[j]) - shift;
+                        s1 += dlt;
+                        s2 = fmaf(dlt, dlt, s2);
+                    }
+                }
+                const float ms = s1 * (1.0f / HID);
+                const float mean = shift + ms;
+                const float var = fmaxf(s2 * (1.0f / HID) - ms * ms, 0.f);
+                const float rstd = 1.0f / sqrtf(var + LN_EPS);
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t acc[32];
+                    tmem_ld32(lane_addr + dcol + c * 32, acc);
+                    tmem_wait_ld();
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        v[j] = (__uint_as_float(acc[j]) - mean) * rstd * S.vec[0][c * 32 + j] + S.vec[1][c * 32 + j];
+                    publish(c, v);
+                }
+            }
+            ++g;
+            // ---- W_e output + bias -> staging -> coalesced store
+            mbar_wait(&S.d_ready[g & 1], (g >> 1) & 1);
+            tc_fence_after();
+            {
+                const uint32_t dcol = (g & 1) ? COL_D1 : COL_D0;
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t acc[32];
+                    tmem_ld32(lane_addr + dcol + c * 32, acc);
+                    tmem_wait_ld();
+                    float o[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(acc[j]) + S.vec[2][c * 32 + j];
+                    store_row_chunk(S.out[c], r, o);
+                }
+            }
+            ++g;
+            tc_fence_before();
+            epi_bar_sync();
+            for (int i = 0; i < 32; ++i) {
+                const int idx = i * 128 + r, rr = idx >> 5, ch = idx & 31;
+                if (row0 + rr < total_rows) {
+                    float4 t = *reinterpret_cast<const float4*>(&S.out[ch >> 3][slab_off(rr, ch & 7)]);
+                    *reinterpret_cast<float4*>(a.hE + (size_t)(row0 + rr) * HID + ch * 4) = t;
+                }
+            }
+            epi_bar_sync();   // staging is rewritten by the next tile
         }
     }
     __syncwarp();
@@ -400,7 +649,19 @@ cudaError_t tc_kernels_init() {
     const int bytes = (int)sizeof(TcSmem) + 1024;
     if ((e = cudaFuncSetAttribute(tc_edge_kernel<TC_UPD>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(tc_edge_kernel<TC_ENC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-    return cudaFuncSetAttribute(tc_edge_kernel<TC_DEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if ((e = cudaFuncSetAttribute(tc_edge_kernel<TC_DEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(tc_edge_feat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcFeatSmem) + 1024);
+}
+
+void launch_tc_edge_feat(const float* atoms, const int* E_idx, const float* D_nb, const int* ridx, const int* cenc,
+                         const float* pos_table, const float* rbf_mu, const float* wimg, const float* ln_g, const float* ln_b,
+                         const float* b_e, float* hE, int N, int sms, cudaStream_t st) {
+    TcFeatArgs a{};
+    a.atoms = atoms; a.E_idx = E_idx; a.D_nb = D_nb; a.ridx = ridx; a.cenc = cenc; a.pos_table = pos_table; a.rbf_mu = rbf_mu;
+    a.wimg = reinterpret_cast<const uint8_t*>(wimg); a.ln_g = ln_g; a.ln_b = ln_b; a.b_e = b_e; a.hE = hE; a.N = N;
+    a.num_tiles = (N * KNB + TC_ROWS - 1) / TC_ROWS;
+    const int grid = a.num_tiles < sms ? a.num_tiles : sms;
+    tc_edge_feat_kernel<<<grid, TC_THREADS, sizeof(TcFeatSmem) + 1024, st>>>(a);
 }
 
 static TcArgs tc_args(float* hE, const int* E_idx, const float* P, int p_stride, const float* Q, int q_stride, const float* maskf,

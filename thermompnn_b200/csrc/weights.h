@@ -116,6 +116,7 @@ struct DecW {
 struct DevLayout {
     int64_t pos_table;      // [66][16]  = embeddings.linear.weight^T + bias
     int64_t feat;           // [edge_embedding KN (416 rows) | W_e KN (128 rows)] 17 chunks
+    int64_t tc_feat;        // the same as tensor-core images: 13 + 4 chunks of 32 KB
     int64_t be;             // W_e bias
     LayerNormW ne;          // norm_edges
     int64_t rbf_mu;         // [16]
