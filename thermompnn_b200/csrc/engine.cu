@@ -81,7 +81,10 @@ struct tmpnn_ctx {
     int last_N = 0;
     float* last_table = nullptr;
     int debug_stop = 0;
-    bool use_tc = true;      // tensor-core edge kernels (TMPNN_TC=0 selects the FP32 SIMT generation, bring-up only)
+    // tensor-core edge kernels; TMPNN_TC=<mask> (bring-up / error localisation only): bit 0 edge_feat, 1 msg, 2 edge_upd;
+    // 0 selects the FP32 SIMT generation everywhere
+    int tc_mask = 7;
+    long long* d_trace = nullptr;   // TMPNN_TC_TRACE=1: phase stamps of enc layer 1's message and edge-update kernels (dev tool)
 
     bool profiling = false;
     std::vector<ProfEntry> prof;
@@ -461,7 +464,9 @@ int tmpnn_create(int device, tmpnn_ctx** out) {
     if ((e = kernels_init()) != cudaSuccess) return bail(std::string("kernels_init: ") + cudaGetErrorString(e));
     if ((e = node_kernels_init()) != cudaSuccess) return bail(std::string("node_kernels_init: ") + cudaGetErrorString(e));
     if ((e = tc_kernels_init()) != cudaSuccess) return bail(std::string("tc_kernels_init: ") + cudaGetErrorString(e));
-    if (const char* env = std::getenv("TMPNN_TC")) ctx->use_tc = std::string(env) != "0";
+    if (const char* env = std::getenv("TMPNN_TC_TRACE"))
+        if (std::atoi(env)) { cudaMalloc(&ctx->d_trace, 2 * 512 * sizeof(long long)); cudaMemset(ctx->d_trace, 0, 2 * 512 * sizeof(long long)); }
+    if (const char* env = std::getenv("TMPNN_TC")) ctx->tc_mask = std::atoi(env) == 1 ? 7 : std::atoi(env);
     *out = ctx;
     return TMPNN_OK;
 }
@@ -605,7 +610,7 @@ int tmpnn_run_batch(tmpnn_ctx* ctx, int32_t B, const int32_t* offsets, const flo
     { LaunchScope ls(ctx, st, "knn");
       launch_knn(ctx->atoms.p, ctx->maskf.p, ctx->pstart.p, ctx->pend.p, N, lmax, ctx->E_idx.p, ctx->D_nb.p, st); }
     if (!stage_done(1)) {
-        if (ctx->use_tc) {
+        if (ctx->tc_mask & 1) {
             LaunchScope ls(ctx, st, "tc_edge_feat");
             launch_tc_edge_feat(ctx->atoms.p, ctx->E_idx.p, ctx->D_nb.p, d_r, d_c, W + L.pos_table, W + L.rbf_mu, W + L.tc_feat,
                                 W + L.ne.g, W + L.ne.b, W + L.be, ctx->hE.p, N, ctx->sm_count, st);
@@ -623,10 +628,10 @@ int tmpnn_run_batch(tmpnn_ctx* ctx, int32_t B, const int32_t* offsets, const flo
                 const float* Pp = l == 0 ? W + e.b1 : ctx->P.p;
                 const float* Qp = l == 0 ? W + L.zeros : ctx->Q.p;
                 const int stride = l == 0 ? 0 : HID;
-                if (ctx->use_tc) {
+                if (ctx->tc_mask & 2) {
                     LaunchScope ls(ctx, st, "tc_enc_msg");
                     launch_tc_msg(false, ctx->hE.p, ctx->E_idx.p, Pp, stride, Qp, stride, ctx->maskf.p, W + e.tc_msg, W + e.b2,
-                                  ctx->Spart.p, N, ctx->sm_count, st);
+                                  ctx->Spart.p, N, ctx->sm_count, st, l == 1 ? ctx->d_trace : nullptr);
                 } else {
                     LaunchScope ls(ctx, st, "enc_msg");
                     launch_msg(npt, false, ctx->hE.p, ctx->E_idx.p, Pp, stride, Qp, stride, ctx->maskf.p, W + e.msg, W + e.b2,
@@ -635,7 +640,7 @@ int tmpnn_run_batch(tmpnn_ctx* ctx, int32_t B, const int32_t* offsets, const flo
             }
             NodeUpdArgs a{};
             a.weights = W; a.w = e.nu; a.Ssum = ctx->Ssum.p; a.cnt = ctx->cnt.p; a.hV = ctx->hV.p; a.hV_copy = nullptr;
-            a.Spart = ctx->use_tc ? ctx->Spart.p : nullptr; a.E_idx = ctx->E_idx.p; a.enc = 1;
+            a.Spart = (ctx->tc_mask & 2) ? ctx->Spart.p : nullptr; a.E_idx = ctx->E_idx.p; a.enc = 1;
             a.maskf = ctx->maskf.p; a.S = d_S; a.N = N;
             a.proj[0] = {e.b11, -1, ctx->P2.p};     // edge update of this layer
             a.proj[1] = {-1, -1, ctx->Q2.p};
@@ -650,10 +655,10 @@ int tmpnn_run_batch(tmpnn_ctx* ctx, int32_t B, const int32_t* offsets, const flo
             }
             a.nproj = 4;
             { LaunchScope ls(ctx, st, "node_update"); launch_node_update(a, ctx->sm_count, st); }
-            if (ctx->use_tc) {
+            if (ctx->tc_mask & 4) {
                 LaunchScope ls(ctx, st, "tc_edge_upd");
                 launch_tc_edge_upd(ctx->hE.p, ctx->E_idx.p, ctx->P2.p, ctx->Q2.p, ctx->maskf.p, W + e.tc_edge, W + e.b12, W + e.b13,
-                                   W + e.n3.g, W + e.n3.b, N, ctx->sm_count, st);
+                                   W + e.n3.g, W + e.n3.b, N, ctx->sm_count, st, (l == 1 && ctx->d_trace) ? ctx->d_trace + 512 : nullptr);
             } else {
                 LaunchScope ls(ctx, st, "edge_upd");
                 launch_edge_upd(npt, ctx->hE.p, ctx->E_idx.p, ctx->P2.p, ctx->Q2.p, W + e.edge, W + e.b12, W + e.b13,
@@ -665,7 +670,7 @@ int tmpnn_run_batch(tmpnn_ctx* ctx, int32_t B, const int32_t* offsets, const flo
     if (!done) {
         for (int l = 0; l < 3 && !done; ++l) {
             const DecW& d = L.dec[l];
-            if (ctx->use_tc) {
+            if (ctx->tc_mask & 2) {
                 LaunchScope ls(ctx, st, "tc_dec_msg");
                 launch_tc_msg(true, ctx->hE.p, ctx->E_idx.p, ctx->P.p, HID, ctx->Q.p, HID, ctx->maskf.p, W + d.tc_msg, W + d.b2,
                               ctx->Spart.p, N, ctx->sm_count, st);
@@ -676,7 +681,7 @@ int tmpnn_run_batch(tmpnn_ctx* ctx, int32_t B, const int32_t* offsets, const flo
             }
             NodeUpdArgs a{};
             a.weights = W; a.w = d.nu; a.Ssum = ctx->Ssum.p; a.cnt = ctx->cnt.p; a.hV = ctx->hV.p;
-            a.Spart = ctx->use_tc ? ctx->Spart.p : nullptr; a.E_idx = ctx->E_idx.p; a.enc = 0;
+            a.Spart = (ctx->tc_mask & 2) ? ctx->Spart.p : nullptr; a.E_idx = ctx->E_idx.p; a.enc = 0;
             a.hV_copy = (l == 1) ? ctx->dec_prev.p : (l == 2 ? ctx->dec_last.p : nullptr);
             a.maskf = ctx->maskf.p; a.S = d_S; a.N = N;
             a.nproj = 0;
@@ -721,6 +726,7 @@ int tmpnn_fetch(tmpnn_ctx* ctx, const char* name, void* host_dst, int64_t bytes)
     else if (s == "dec1") { src = ctx->dec_prev.p; sz = n * HID * 4; }
     else if (s == "dec2") { src = ctx->dec_last.p; sz = n * HID * 4; }
     else if (s == "table") { src = ctx->last_table; sz = n * 21 * 4; }
+    else if (s == "tc_trace" && ctx->d_trace) { src = ctx->d_trace; sz = 2 * 512 * sizeof(long long); }
     else return fail(ctx, TMPNN_E_NOTFOUND, "tmpnn_fetch: unknown tensor '" + s + "'");
     if ((size_t)bytes != sz)
         return fail(ctx, TMPNN_E_RANGE, "tmpnn_fetch: '" + s + "' is " + std::to_string(sz) + " bytes, caller gave " + std::to_string(bytes));

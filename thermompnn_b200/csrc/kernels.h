@@ -59,12 +59,14 @@ void launch_edge_upd(int npt, float* hE, const int* E_idx, const float* P, const
                      const float* b12, const float* b13, const float* ln_g, const float* ln_b, int N,
                      cudaStream_t st);
 void launch_tc_edge_upd(float* hE, const int* E_idx, const float* P, const float* Q, const float* maskf, const float* wimg,
-                        const float* b12, const float* b13, const float* ln_g, const float* ln_b, int N, int sms, cudaStream_t st);
+                        const float* b12, const float* b13, const float* ln_g, const float* ln_b, int N, int sms, cudaStream_t st,
+                        long long* trace = nullptr);
 void launch_tc_edge_feat(const float* atoms, const int* E_idx, const float* D_nb, const int* ridx, const int* cenc,
                          const float* pos_table, const float* rbf_mu, const float* wimg, const float* ln_g, const float* ln_b,
                          const float* b_e, float* hE, int N, int sms, cudaStream_t st);
 void launch_tc_msg(bool dec, const float* hE, const int* E_idx, const float* P, int p_stride, const float* Q, int q_stride,
-                   const float* maskf, const float* wimg, const float* b2, float* Spart, int N, int sms, cudaStream_t st);
+                   const float* maskf, const float* wimg, const float* b2, float* Spart, int N, int sms, cudaStream_t st,
+                   long long* trace = nullptr);
 void launch_node_update(const NodeUpdArgs& a, int sms, cudaStream_t st);
 void launch_head(const HeadArgs& a, cudaStream_t st);
 

@@ -70,6 +70,14 @@ __device__ __forceinline__ void load_row_chunk(float (&v)[32], const float* slab
         v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
     }
 }
+// the same for an activation chunk filled by per-row bulk copies (row pitch ACT_PITCH floats, no swizzle)
+__device__ __forceinline__ void load_act_row(float (&v)[32], const float* chunk, int r) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float4 t = *reinterpret_cast<const float4*>(chunk + r * 36 + j * 4);
+        v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+    }
+}
 __device__ __forceinline__ void store_row_chunk(float* slab, int r, const float (&v)[32]) {
 #pragma unroll
     for (int j = 0; j < 8; ++j)
@@ -99,8 +107,36 @@ __device__ __forceinline__ void publish_A_chunk(uint32_t lane_addr, int c, const
 // ENC/DEC write the column sums of every 16-row sub-block of the edge array (a residue is exactly three of them)
 // into Spart[residue][0..2][128]; node_update adds the three parts in order, so the neighbour sum is deterministic
 // and independent of where the residue sits in the batch.  W3 is applied there, after the sum.
+//
+// Warp roles (352 threads): warps 0-7 epilogue (two sets of four; set s handles 32-column chunks c with c%2 == s,
+// thread = edge row = TMEM lane), warp 8 MMA issuer, warp 9 weight producer, warp 10 activation producer.
+// Everything gathered per row (h_E input, Q_j, the residual) flows through ONE ring of [128 rows][32 cols] chunks.
+// MMA schedule: K-chunk by K-chunk as the epilogue publishes them (short tail after the last chunk); inside a chunk
+// the two small correction products (A_lo.B_hi, A_hi.B_lo) go first, then A_hi.B_hi.
 // ---------------------------------------------------------------------------------------------------------
 enum TcKind { TC_UPD = 0, TC_ENC = 1, TC_DEC = 2 };
+
+constexpr int T2_THREADS = 352;
+constexpr int T2_NW = 3, T2_NACT = 4;
+constexpr int ACT_PITCH = 36;          // floats per row of an activation chunk: 128 B of data + 16 B pad, so that thread-per-row
+                                       // 16-byte reads hit 8 different bank groups per quarter-warp (9r mod 8 = r mod 8)
+constexpr uint32_t T2_HALF = 16384;   // one [128 n][32 k] tf32 plane
+
+struct __align__(1024) Tc2Smem {
+    uint8_t w[T2_NW][2 * T2_HALF];       // 96 KB  weight chunks: B_hi plane | B_lo plane
+    float act[T2_NACT][TC_ROWS * ACT_PITCH];   // 72 KB  gathered activation chunks, row pitch 144 B
+    float out[2][TC_ROWS * 32];          // 32 KB  UPD: output staging, one slab per epilogue set
+    float p[2][4][HID];                  // P rows of the residues the tile touches, double-buffered by tile parity
+    float wrow[2][TC_ROWS];
+    float mrow[2][TC_ROWS];
+    float vec[4][HID];
+    float2 lnx[2][TC_ROWS];              // LayerNorm partial (mean, M2) exchange between the two sets
+    int jidx[TC_ROWS];
+    uint64_t w_full[T2_NW], w_empty[T2_NW];
+    uint64_t act_full[T2_NACT], act_empty[T2_NACT];
+    uint64_t a_ready[4], d_ready[2];
+    uint32_t tmem_base;
+};
 
 struct TcArgs {
     float* hE;              // [N*48][128]; UPD updates it in place
@@ -108,14 +144,19 @@ struct TcArgs {
     const float* P; int p_stride;   // per-residue projection of h_V[i] (+bias); stride 0 = one shared row
     const float* Q; int q_stride;   // per-residue projection of h_V[j] (R_j for DEC)
     const float* maskf;     // [N]
-    const uint8_t* wimg;    // weight image
+    const uint8_t* wimg;    // weight image: per matrix 4 chunks of (hi 16 KB | lo 16 KB)
     const float* v0;        // UPD: b12   ENC/DEC: b2
     const float* v1;        // UPD: b13
     const float* v2;        // UPD: LN gain
     const float* v3;        // UPD: LN shift
     float* Spart;           // ENC/DEC: [N][3][128]
+    long long* trace;       // optional (TMPNN_TC_TRACE=1): clock64() phase stamps of block 0, 32 slots per tile
     int N, num_tiles;
 };
+
+// phase stamp: slot layout per tile = [0..15] epilogue set 0 (warp 0), [16..23] set 1 (warp 4), [24..31] MMA warp
+#define TC_STAMP(ti_, slot_) \
+    do { if (a.trace && blockIdx.x == 0 && lane == 0 && (ti_) < 16) a.trace[(ti_) * 32 + (slot_)] = clock64(); } while (0)
 
 // Column sums over each 16-row half of a warp (half-warps never straddle a residue: 48 = 3 x 16).
 // On return lane l holds, for its half, the sums of columns 2*(l&15) and 2*(l&15)+1 in v[0], v[1].
@@ -132,47 +173,48 @@ __device__ __forceinline__ void halfwarp_colsum32(float (&v)[32], int lane) {
     }
 }
 
+__device__ __forceinline__ void named_bar(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
 template <int KIND>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_kernel(TcArgs a) {
+__global__ void __launch_bounds__(T2_THREADS, 1) tc_edge_kernel(TcArgs a) {
     constexpr int STAGES = (KIND == TC_UPD) ? 3 : 2;
-    constexpr int WCHUNKS = 4 * STAGES;
+    constexpr int ACT_PER_TILE = (KIND == TC_UPD) ? 12 : 8;   // input x4, Q x4, (residual x4)
     extern __shared__ uint8_t smem_raw[];
-    TcSmem& S = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    Tc2Smem& S = *reinterpret_cast<Tc2Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int N = a.N, num_tiles = a.num_tiles;
     const int total_rows = N * KNB;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < TC_WSLOTS; ++i) { mbar_init(&S.w_full[i], 1); mbar_init(&S.w_empty[i], 1); }
+        for (int i = 0; i < T2_NW; ++i) { mbar_init(&S.w_full[i], 1); mbar_init(&S.w_empty[i], 1); }
+        for (int i = 0; i < T2_NACT; ++i) { mbar_init(&S.act_full[i], 64); mbar_init(&S.act_empty[i], 128); }
         for (int i = 0; i < 4; ++i) mbar_init(&S.a_ready[i], 128);
-        for (int i = 0; i < 2; ++i) { mbar_init(&S.d_ready[i], 1); mbar_init(&S.q_full[i], 32); mbar_init(&S.q_empty[i], 128); }
-        mbar_init(&S.he_full, 64);
-        mbar_init(&S.he_empty, 128);
+        for (int i = 0; i < 2; ++i) mbar_init(&S.d_ready[i], 1);
         fence_barrier_init();
     }
-    for (int i = threadIdx.x; i < HID; i += TC_THREADS) {
+    for (int i = threadIdx.x; i < HID; i += T2_THREADS) {
         S.vec[0][i] = a.v0[i];
         if (KIND == TC_UPD) { S.vec[1][i] = a.v1[i]; S.vec[2][i] = a.v2[i]; S.vec[3][i] = a.v3[i]; }
     }
-    if (warp == 4) tmem_alloc<512>(&S.tmem_base);
+    if (warp == 8) tmem_alloc<512>(&S.tmem_base);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = S.tmem_base;
 
-    if (warp == 5) {
+    if (warp == 9) {
         // ---------------- weight producer ----------------
         if (lane == 0) {
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
-                for (int c = 0; c < WCHUNKS; ++c, ++it) {
-                    const uint32_t slot = it % TC_WSLOTS, use = it / TC_WSLOTS;
-                    if (use > 0) mbar_wait(&S.w_empty[slot], (use - 1) & 1);
-                    mbar_arrive_expect_tx(&S.w_full[slot], TC_WCHUNK_BYTES);
-                    bulk_g2s(S.wring[slot], a.wimg + (size_t)c * TC_WCHUNK_BYTES, TC_WCHUNK_BYTES, &S.w_full[slot]);
+                for (int c = 0; c < 4 * STAGES; ++c, ++it) {
+                    const uint32_t s = it % T2_NW, u = it / T2_NW;
+                    if (u > 0) mbar_wait(&S.w_empty[s], (u - 1) & 1);
+                    mbar_arrive_expect_tx(&S.w_full[s], 2 * T2_HALF);
+                    bulk_g2s(S.w[s], a.wimg + (size_t)c * 2 * T2_HALF, 2 * T2_HALF, &S.w_full[s]);
                 }
         }
-    } else if (warp == 4) {
+    } else if (warp == 8) {
         // ---------------- MMA issuer ----------------
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(128, 128);
@@ -181,159 +223,206 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_kernel(TcArgs a) {
                 for (int l = 0; l < STAGES; ++l, ++g) {
                     const uint32_t d = tmem + ((g & 1) ? COL_D1 : COL_D0);
                     for (int c = 0; c < 4; ++c, ++it) {
-                        const uint32_t slot = it % TC_WSLOTS;
+                        const uint32_t sw = it % T2_NW;
                         mbar_wait(&S.a_ready[c], g & 1);
-                        mbar_wait(&S.w_full[slot], (it / TC_WSLOTS) & 1);
+                        if (c == 0) TC_STAMP(g / STAGES, 24 + 2 * l);
+                        mbar_wait(&S.w_full[sw], (it / T2_NW) & 1);
                         tc_fence_after();
-                        const uint32_t wb = smem_u32(S.wring[slot]);
+                        const uint32_t bh = smem_u32(S.w[sw]), bl = bh + T2_HALF;
+                        // per K-chunk: the two small correction products first, then hi.hi (the accumulator truncates on
+                        // every add; small terms are best summed among themselves before they meet the large ones)
 #pragma unroll
                         for (int s = 0; s < 4; ++s) {
                             const uint32_t koff = c * 32 + s * 8;
-                            const uint64_t bh = make_desc_sw128(wb + s * 32), bl = make_desc_sw128(wb + 16384 + s * 32);
-                            mma_tf32_ts(d, tmem + COL_AHI + koff, bh, idesc, (c | s) != 0);
-                            mma_tf32_ts(d, tmem + COL_ALO + koff, bh, idesc, 1);
-                            mma_tf32_ts(d, tmem + COL_AHI + koff, bl, idesc, 1);
+                            mma_tf32_ts(d, tmem + COL_ALO + koff, make_desc_sw128(bh + s * 32), idesc, (c | s) != 0);
+                            mma_tf32_ts(d, tmem + COL_AHI + koff, make_desc_sw128(bl + s * 32), idesc, 1);
                         }
-                        mma_commit(&S.w_empty[slot]);
-                        if (c == 3) mma_commit(&S.d_ready[g & 1]);
+#pragma unroll
+                        for (int s = 0; s < 4; ++s)
+                            mma_tf32_ts(d, tmem + COL_AHI + c * 32 + s * 8, make_desc_sw128(bh + s * 32), idesc, 1);
+                        mma_commit(&S.w_empty[sw]);
                     }
+                    mma_commit(&S.d_ready[g & 1]);
+                    TC_STAMP(g / STAGES, 25 + 2 * l);
                 }
         }
-    } else if (warp == 6) {
+    } else if (warp == 10) {
         // ---------------- activation producer ----------------
-        uint32_t ti = 0, qit = 0;
+        // Every lane owns rows lane, lane+32, lane+64, lane+96 of the tile and copies their 128-byte chunk slices with
+        // eight 16-byte cp.async each (h_E rows, or the neighbour's Q row): no index math inside the copy loop.
+        // (One 128-byte bulk copy per row was measured 3x slower: too fine-grained for the TMA unit.)
+        uint32_t ti = 0, k = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
             const int row0 = tile * TC_ROWS;
             const int node_lo = row0 / KNB;
-            if (ti > 0) mbar_wait(&S.he_empty, (ti - 1) & 1);
-            for (int r = 0; r < TC_ROWS; ++r) {          // one row per iteration, lane = 16-byte chunk
-                float* dst = &S.hE[lane >> 3][slab_off(r, lane & 7)];
-                if (row0 + r < total_rows) cp_async16(dst, a.hE + (size_t)(row0 + r) * HID + lane * 4);
-                else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                int node = node_lo + i; node = node < N ? node : N - 1;
-                cp_async16(&S.p[i][lane * 4], a.P + (size_t)node * a.p_stride + lane * 4);
-            }
+            const uint32_t mb = ti & 1;
+            int jrow[4];
+            bool okrow[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int r = lane + 32 * i, row = row0 + r;
                 int j = N - 1;
                 float w = 0.f, mi = 0.f;
-                if (row < total_rows) {
+                okrow[i] = row < total_rows;
+                if (okrow[i]) {
                     const int node = row / KNB;
                     mi = a.maskf[node];
                     j = a.E_idx[row];
                     if (j < 0) j = node;                                   // unused slot: a finite dummy
                     else w = (KIND == TC_ENC) ? mi * a.maskf[j] : 1.0f;    // mask_attend (protein_mpnn_utils.py:1232-1233)
                 }
-                S.jidx[r] = j; S.wrow[r] = w; S.mrow[r] = mi;
+                jrow[i] = j; S.wrow[mb][r] = w; S.mrow[mb][r] = mi;
             }
-            cp_async_arrive_noinc(&S.he_full);
-            mbar_arrive(&S.he_full);
-            __syncwarp();
-            for (int c = 0; c < 4; ++c, ++qit) {
-                const uint32_t b = qit & 1, use = qit >> 1;
-                if (use > 0) mbar_wait(&S.q_empty[b], (use - 1) & 1);
-                for (int i = 0; i < 32; ++i) {           // 4 rows per iteration, 8 lanes per row
-                    const int r = i * 4 + (lane >> 3), ch = lane & 7;
-                    cp_async16(&S.q[b][slab_off(r, ch)], a.Q + (size_t)S.jidx[r] * a.q_stride + c * 32 + ch * 4);
+            auto chunk = [&](int c, bool gather_q, bool with_p) {
+                const uint32_t s = k % T2_NACT, u = k / T2_NACT;
+                if (u > 0) mbar_wait(&S.act_empty[s], (u - 1) & 1);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = lane + 32 * i;
+                    float* dst = &S.act[s][r * ACT_PITCH];
+                    if (gather_q || okrow[i]) {
+                        const float* src = gather_q ? a.Q + (size_t)jrow[i] * a.q_stride + c * 32
+                                                    : a.hE + (size_t)(row0 + r) * HID + c * 32;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) cp_async16_ca(dst + q * 4, src + q * 4);
+                    } else {                                   // row past the end of the edge array
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) reinterpret_cast<float4*>(dst)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
                 }
-                cp_async_arrive_noinc(&S.q_full[b]);
-            }
+                if (with_p) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        int node = node_lo + i; node = node < N ? node : N - 1;
+                        cp_async16_ca(&S.p[mb][i][lane * 4], a.P + (size_t)node * a.p_stride + lane * 4);
+                    }
+                }
+                cp_async_arrive_noinc(&S.act_full[s]);          // fires when this lane's copies have landed
+                mbar_arrive(&S.act_full[s]);                    // releases this lane's plain stores (zeros, wrow/mrow)
+                ++k;
+            };
+            for (int c = 0; c < 4; ++c) chunk(c, false, c == 0);
+            for (int c = 0; c < 4; ++c) chunk(c, true, false);
+            if (KIND == TC_UPD)
+                for (int c = 0; c < 4; ++c) chunk(c, false, false);
         }
         cp_async_wait<0>();
     } else {
-        // ---------------- epilogue: thread <-> edge row ----------------
-        const int r = threadIdx.x;                        // 0..127
-        const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
-        uint32_t ti = 0, g = 0, qit = 0;
+        // ---------------- epilogue: thread <-> (edge row, chunk parity) ----------------
+        const int set = warp >> 2, quad = warp & 3;
+        const int r = quad * 32 + lane;                    // 0..127
+        const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
+        uint32_t ti = 0, g = 0;
+        auto act_wait = [&](uint32_t k) -> const float* {
+            const uint32_t s = k % T2_NACT;
+            mbar_wait(&S.act_full[s], (k / T2_NACT) & 1);
+            return S.act[s];
+        };
+        auto act_release = [&](uint32_t k) { mbar_arrive(&S.act_empty[k % T2_NACT]); };
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
             const int row0 = tile * TC_ROWS;
             const int row = row0 + r;
+            const uint32_t k0 = ti * ACT_PER_TILE, mb = ti & 1;
             int node_l = row / KNB - row0 / KNB;
             node_l = node_l > 3 ? 3 : node_l;
+            const int sb0 = (quad == 0) ? (set ? 16 : 0) : 64;   // only warps 0 and 4 stamp (slot >= 32 is discarded below)
+#define EPI_STAMP(n_) do { if (sb0 < 32) TC_STAMP(ti, sb0 + (n_)); } while (0)
+            EPI_STAMP(0);
             // ---- input: h_E rows -> A
-            mbar_wait(&S.he_full, ti & 1);
-            const float w_r = S.wrow[r], m_i = S.mrow[r];
-            for (int c = 0; c < 4; ++c) {
+            float w_r = 0.f, m_i = 0.f;
+            for (int c = set; c < 4; c += 2) {
+                const float* slab = act_wait(k0 + c);
                 float v[32];
-                load_row_chunk(v, S.hE[c], r);
+                load_act_row(v, slab, r);
+                act_release(k0 + c);
                 publish_A_chunk(lane_addr, c, v, &S.a_ready[c]);
             }
-            if (KIND != TC_UPD) mbar_arrive(&S.he_empty);      // staging tile is free: the next one can stream in
+            w_r = S.wrow[mb][r];
+            m_i = S.mrow[mb][r];
+            EPI_STAMP(1);
             // ---- stage 1: gathered projections, GELU
             mbar_wait(&S.d_ready[g & 1], (g >> 1) & 1);
             tc_fence_after();
+            EPI_STAMP(2);
             {
                 const uint32_t dcol = (g & 1) ? COL_D1 : COL_D0;
-                for (int c = 0; c < 4; ++c, ++qit) {
-                    const uint32_t b = qit & 1;
+                for (int c = set; c < 4; c += 2) {
                     uint32_t acc[32];
                     tmem_ld32(lane_addr + dcol + c * 32, acc);
-                    mbar_wait(&S.q_full[b], (qit >> 1) & 1);
+                    const float* slab = act_wait(k0 + 4 + c);
                     float qv[32], v[32];
-                    load_row_chunk(qv, S.q[b], r);
+                    load_act_row(qv, slab, r);
+                    act_release(k0 + 4 + c);
                     tmem_wait_ld();
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const float pj = S.p[node_l][c * 32 + j];
+                        const float pj = S.p[mb][node_l][c * 32 + j];
                         const float pre = (KIND == TC_DEC) ? fmaf(m_i, __uint_as_float(acc[j]) + qv[j], pj)
                                                            : (__uint_as_float(acc[j]) + pj + qv[j]);
-                        v[j] = gelu_erf(pre);
+                        v[j] = gelu_fast(pre);
                     }
-                    mbar_arrive(&S.q_empty[b]);
                     publish_A_chunk(lane_addr, c, v, &S.a_ready[c]);
                 }
             }
             ++g;
+            EPI_STAMP(3);
             if (KIND == TC_UPD) {
                 // ---- stage 2: + b12, GELU
                 mbar_wait(&S.d_ready[g & 1], (g >> 1) & 1);
                 tc_fence_after();
+                EPI_STAMP(4);
                 {
                     const uint32_t dcol = (g & 1) ? COL_D1 : COL_D0;
-                    for (int c = 0; c < 4; ++c) {
+                    for (int c = set; c < 4; c += 2) {
                         uint32_t acc[32];
                         tmem_ld32(lane_addr + dcol + c * 32, acc);
                         tmem_wait_ld();
                         float v[32];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(__uint_as_float(acc[j]) + S.vec[0][c * 32 + j]);
+                        for (int j = 0; j < 32; ++j) v[j] = gelu_fast(__uint_as_float(acc[j]) + S.vec[0][c * 32 + j]);
                         publish_A_chunk(lane_addr, c, v, &S.a_ready[c]);
                     }
                 }
                 ++g;
-                // ---- stage 3: + b13 + h_E (residual), LayerNorm over the row (thread-local), back into the staging tile
+                EPI_STAMP(5);
+                // ---- stage 3: + b13 + residual, LayerNorm over the row (two threads per row), coalesced write-back
                 mbar_wait(&S.d_ready[g & 1], (g >> 1) & 1);
                 tc_fence_after();
+                EPI_STAMP(6);
                 {
                     const uint32_t dcol = (g & 1) ? COL_D1 : COL_D0;
                     float shift = 0.f, s1 = 0.f, s2 = 0.f;
-                    for (int c = 0; c < 4; ++c) {
+                    for (int c = set; c < 4; c += 2) {
                         uint32_t acc[32];
                         tmem_ld32(lane_addr + dcol + c * 32, acc);
+                        const float* slab = act_wait(k0 + 8 + c);
                         float old[32];
-                        load_row_chunk(old, S.hE[c], r);
+                        load_act_row(old, slab, r);
+                        act_release(k0 + 8 + c);
                         tmem_wait_ld();
-                        if (c == 0) shift = __uint_as_float(acc[0]) + S.vec[1][0] + old[0];
+                        if (c == set) shift = __uint_as_float(acc[0]) + S.vec[1][c * 32] + old[0];
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            float x = __uint_as_float(acc[j]) + S.vec[1][c * 32 + j] + old[j];
+                            const float x = __uint_as_float(acc[j]) + S.vec[1][c * 32 + j] + old[j];
                             acc[j] = __float_as_uint(x);
-                            float dlt = x - shift;
+                            const float dlt = x - shift;
                             s1 += dlt;
                             s2 = fmaf(dlt, dlt, s2);
                         }
                         tmem_st32(lane_addr + dcol + c * 32, acc);
                     }
                     tmem_wait_st();
-                    const float ms = s1 * (1.0f / HID);
-                    const float mean = shift + ms;
-                    const float var = fmaxf(s2 * (1.0f / HID) - ms * ms, 0.f);
+                    // this thread's 64 values: mean_a, M2_a; combine with the partner's (Chan et al.)
+                    const float mean_a = shift + s1 * (1.0f / 64.0f);
+                    const float m2_a = fmaxf(s2 - s1 * s1 * (1.0f / 64.0f), 0.f);
+                    S.lnx[set][r] = make_float2(mean_a, m2_a);
+                    named_bar(3, 256);
+                    const float2 ob = S.lnx[set ^ 1][r];
+                    const float dm = mean_a - ob.x;
+                    const float mean = 0.5f * (mean_a + ob.x);
+                    const float var = (m2_a + ob.y + 32.0f * dm * dm) * (1.0f / HID);
                     const float rstd = 1.0f / sqrtf(var + LN_EPS);
-                    for (int c = 0; c < 4; ++c) {
+                    for (int c = set; c < 4; c += 2) {
                         uint32_t xv[32];
                         tmem_ld32(lane_addr + dcol + c * 32, xv);
                         tmem_wait_ld();
@@ -341,37 +430,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_kernel(TcArgs a) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
                             o[j] = (__uint_as_float(xv[j]) - mean) * rstd * S.vec[2][c * 32 + j] + S.vec[3][c * 32 + j];
-                        store_row_chunk(S.hE[c], r, o);
+                        store_row_chunk(S.out[set], r, o);
+                        named_bar(1 + set, 128);
+                        for (int i = 0; i < 8; ++i) {                       // 128 rows x 128 B, coalesced
+                            const int idx = i * 128 + r, rr = idx >> 3, ch = idx & 7;
+                            if (row0 + rr < total_rows)
+                                *reinterpret_cast<float4*>(a.hE + (size_t)(row0 + rr) * HID + c * 32 + ch * 4) =
+                                    *reinterpret_cast<const float4*>(&S.out[set][slab_off(rr, ch)]);
+                        }
+                        named_bar(1 + set, 128);
                     }
                 }
                 ++g;
                 tc_fence_before();
-                epi_bar_sync();
-                // coalesced write-back of the tile: 4096 16-byte chunks
-                for (int i = 0; i < 32; ++i) {
-                    const int idx = i * 128 + r, rr = idx >> 5, ch = idx & 31;
-                    if (row0 + rr < total_rows) {
-                        float4 t = *reinterpret_cast<const float4*>(&S.hE[ch >> 3][slab_off(rr, ch & 7)]);
-                        *reinterpret_cast<float4*>(a.hE + (size_t)(row0 + rr) * HID + ch * 4) = t;
-                    }
-                }
-                mbar_arrive(&S.he_empty);
+                EPI_STAMP(7);
             } else {
-                // ---- stage 2 (final): + b2, GELU, weight, per-residue column sums of this warp's 32 rows
+                // ---- stage 2 (final): + b2, GELU, weight, per-residue column sums of each 16-row half-warp
                 mbar_wait(&S.d_ready[g & 1], (g >> 1) & 1);
                 tc_fence_after();
+                EPI_STAMP(4);
                 {
                     const uint32_t dcol = (g & 1) ? COL_D1 : COL_D0;
-                    const int sb = (row0 + warp * 32) / 16 + (lane >> 4);   // 16-row sub-block of the edge array
+                    const int sb = (row0 + quad * 32) / 16 + (lane >> 4);   // 16-row sub-block of the edge array
                     const int node = sb / 3, part = sb - node * 3;
-                    for (int c = 0; c < 4; ++c) {
+                    for (int c = set; c < 4; c += 2) {
                         uint32_t acc[32];
                         tmem_ld32(lane_addr + dcol + c * 32, acc);
                         tmem_wait_ld();
                         float gv[32];
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            const float gl = gelu_erf(__uint_as_float(acc[j]) + S.vec[0][c * 32 + j]);
+                            const float gl = gelu_fast(__uint_as_float(acc[j]) + S.vec[0][c * 32 + j]);
                             gv[j] = (w_r != 0.f) ? w_r * gl : 0.f;
                         }
                         halfwarp_colsum32(gv, lane);
@@ -381,13 +470,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_kernel(TcArgs a) {
                     }
                 }
                 ++g;
+                tc_fence_before();
+                EPI_STAMP(7);
             }
         }
     }
     __syncwarp();
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc<512>(tmem);
+    if (warp == 8) tmem_dealloc<512>(tmem);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -646,7 +737,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_feat_kernel(TcFeatArgs 
 
 cudaError_t tc_kernels_init() {
     cudaError_t e;
-    const int bytes = (int)sizeof(TcSmem) + 1024;
+    const int bytes = (int)sizeof(Tc2Smem) + 1024;
     if ((e = cudaFuncSetAttribute(tc_edge_kernel<TC_UPD>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(tc_edge_kernel<TC_ENC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(tc_edge_kernel<TC_DEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
@@ -675,20 +766,22 @@ static TcArgs tc_args(float* hE, const int* E_idx, const float* P, int p_stride,
 }
 
 void launch_tc_edge_upd(float* hE, const int* E_idx, const float* P, const float* Q, const float* maskf, const float* wimg,
-                        const float* b12, const float* b13, const float* ln_g, const float* ln_b, int N, int sms, cudaStream_t st) {
+                        const float* b12, const float* b13, const float* ln_g, const float* ln_b, int N, int sms, cudaStream_t st,
+                        long long* trace) {
     TcArgs a = tc_args(hE, E_idx, P, HID, Q, HID, maskf, wimg, N);
-    a.v0 = b12; a.v1 = b13; a.v2 = ln_g; a.v3 = ln_b;
+    a.v0 = b12; a.v1 = b13; a.v2 = ln_g; a.v3 = ln_b; a.trace = trace;
     const int grid = a.num_tiles < sms ? a.num_tiles : sms;
-    tc_edge_kernel<TC_UPD><<<grid, TC_THREADS, sizeof(TcSmem) + 1024, st>>>(a);
+    tc_edge_kernel<TC_UPD><<<grid, T2_THREADS, sizeof(Tc2Smem) + 1024, st>>>(a);
 }
 
 void launch_tc_msg(bool dec, const float* hE, const int* E_idx, const float* P, int p_stride, const float* Q, int q_stride,
-                   const float* maskf, const float* wimg, const float* b2, float* Spart, int N, int sms, cudaStream_t st) {
+                   const float* maskf, const float* wimg, const float* b2, float* Spart, int N, int sms, cudaStream_t st,
+                   long long* trace) {
     TcArgs a = tc_args(const_cast<float*>(hE), E_idx, P, p_stride, Q, q_stride, maskf, wimg, N);
-    a.v0 = b2; a.Spart = Spart;
+    a.v0 = b2; a.Spart = Spart; a.trace = trace;
     const int grid = a.num_tiles < sms ? a.num_tiles : sms;
-    if (dec) tc_edge_kernel<TC_DEC><<<grid, TC_THREADS, sizeof(TcSmem) + 1024, st>>>(a);
-    else tc_edge_kernel<TC_ENC><<<grid, TC_THREADS, sizeof(TcSmem) + 1024, st>>>(a);
+    if (dec) tc_edge_kernel<TC_DEC><<<grid, T2_THREADS, sizeof(Tc2Smem) + 1024, st>>>(a);
+    else tc_edge_kernel<TC_ENC><<<grid, T2_THREADS, sizeof(Tc2Smem) + 1024, st>>>(a);
 }
 
 }  // namespace tmpnn

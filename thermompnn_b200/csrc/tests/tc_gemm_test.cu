@@ -111,6 +111,27 @@ __global__ void __launch_bounds__(192) gemm_kernel(const float* __restrict__ A, 
     if (warp == 4) tmem_dealloc<512>(tmem);
 }
 
+__global__ void gelu_check_kernel(float* out, int n, float lo, float hi) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { float x = lo + (hi - lo) * (float)i / (float)(n - 1); out[2 * i] = x; out[2 * i + 1] = gelu_fast(x); }
+}
+static int check_gelu() {
+    const int n = 1 << 20;
+    float* d; cudaMalloc(&d, 2 * n * sizeof(float));
+    gelu_check_kernel<<<n / 256, 256>>>(d, n, -9.f, 9.f);
+    std::vector<float> h(2 * n);
+    cudaMemcpy(h.data(), d, 2 * n * sizeof(float), cudaMemcpyDeviceToHost);
+    double maxerr = 0, maxrel = 0;
+    for (int i = 0; i < n; ++i) {
+        double x = h[2 * i], ref = 0.5 * x * (1.0 + erf(x / sqrt(2.0)));
+        double e = fabs(h[2 * i + 1] - ref);
+        maxerr = fmax(maxerr, e);
+        maxrel = fmax(maxrel, e / fmax(fabs(x), 1.0));
+    }
+    printf("gelu_fast on [-9,9]: max abs err %.3e, max err / max(1,|x|) %.3e\n", maxerr, maxrel);
+    cudaFree(d);
+    return (maxerr < 1.5e-6 && maxrel < 3e-7) ? 0 : 1;
+}
 static float trunc_tf32(float x) { uint32_t u; memcpy(&u, &x, 4); u &= 0xffffe000u; memcpy(&x, &u, 4); return x; }
 int run(bool exact_inputs) {
     std::vector<float> A(M * K), W(N * K), D(M * N), img(2 * N * K);
@@ -169,7 +190,7 @@ int run(bool exact_inputs) {
     return rc;
 }
 int main() {
-    int rc = run(false) | run(true);
+    int rc = run(false) | run(true) | check_gelu();
     printf(rc ? "FAIL\n" : "PASS\n");
     return rc;
 }

@@ -160,6 +160,12 @@ class Engine:
         self._check(self._lib.tmpnn_fetch(self._ctx, name.encode(), a.ctypes.data, a.nbytes))
         return a
 
+    def fetch_trace(self) -> np.ndarray:
+        """TMPNN_TC_TRACE=1 only: [2 kernels][16 tiles][32 slots] clock64 stamps of block 0."""
+        a = np.zeros((2, 16, 32), dtype=np.int64)
+        self._check(self._lib.tmpnn_fetch(self._ctx, b"tc_trace", a.ctypes.data, a.nbytes))
+        return a
+
     def set_debug_stop(self, stage: int):
         self._check(self._lib.tmpnn_set_debug_stop(self._ctx, stage))
 
