@@ -142,3 +142,27 @@ def test_error_codes(gpu_model):
     with pytest.raises(engine.EngineError, match="weights not loaded"):
         fresh.run(p.offsets, p.X, p.S, p.residue_idx, p.chain_enc, p.mask)
     fresh.close()
+
+
+def test_custom_inference_matches_published_csv(gpu_model):
+    """The reference's own known-answer file (examples/ThermoMPNN_inference_2OCJ.csv, made on the authors' GPU: pins ~1e-3)
+    and, tighter, the live-reference fixture -- through the PDB parser, SSM enumeration and CSV frame of the CLI entry."""
+    import os
+    import pandas as pd
+    from conftest import GOLDEN
+    from thermompnn_b200 import custom_inference as ci
+    df, pdb_id = ci.run(os.path.join(GOLDEN, "2OCJ.pdb"), "A", gpu_model)
+    ref = pd.read_csv(os.path.join(GOLDEN, "ref_2OCJ_A_published.csv"), index_col=0)
+    got = df["ddG_pred"].astype(float).values
+    assert np.abs(got - ref["ddG_pred"].values).max() <= 1e-3
+    d, _ = load_case("2OCJ_A")
+    assert np.abs(got.reshape(194, 20) - d["ddG"]).max() <= TOL
+    assert (df["position"].astype(int).values == ref["position"].values).all()
+
+
+def test_sharded_tables_single_rank(gpu_model):
+    from thermompnn_b200.sharding import sharded_tables
+    pdbs = [synth(30, 1), synth(64, 2), synth(47, 3)]
+    out = sharded_tables(pdbs, gpu_model.head_tables)
+    for a, b in zip(out, gpu_model.head_tables(pdbs)):
+        assert np.array_equal(a, b)

@@ -94,6 +94,25 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         : "memory");
 }
 
+// 32 lanes x 16 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+
 // ---- descriptors ----------------------------------------------------------------------------------------------------
 // Shared-memory matrix descriptor (sm_100 format): K-major operand, SWIZZLE_128B, 8-row groups 1024 B apart.
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
@@ -117,6 +136,31 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
         "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// The same with the descriptor given as (low word, high word).  The issuing thread is a single lane running at
+// ~0.2 IPC: every scalar instruction between two MMAs costs ~5 cycles of issue rate (measured: 67 cycles/MMA with
+// precomputed descriptors vs 145-190 with per-MMA descriptor arithmetic, csrc/tests/tc_mma_timing.cu), so callers
+// keep desc_lo = base + compile-time offset and a constant desc_hi.
+__device__ __forceinline__ void mma_tf32_ts_lh(uint32_t d_tmem, uint32_t a_tmem, uint32_t desc_lo, uint32_t desc_hi, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\t"
+        "setp.eq.u32 p, 1, 1;\n\t"
+        "mov.b64 bd, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %4, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "r"(desc_lo), "r"(desc_hi), "r"(idesc)
+        : "memory");
+}
+__device__ __forceinline__ void mma_tf32_ts_lh_init(uint32_t d_tmem, uint32_t a_tmem, uint32_t desc_lo, uint32_t desc_hi, uint32_t idesc) {
+    asm volatile(   // D = A.B (accumulator overwritten)
+        "{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\t"
+        "setp.eq.u32 p, 1, 0;\n\t"
+        "mov.b64 bd, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %4, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "r"(desc_lo), "r"(desc_hi), "r"(idesc)
+        : "memory");
+}
+constexpr uint32_t DESC_SW128_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B
+__device__ __forceinline__ uint32_t desc_sw128_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+
 // Arrive on an mbarrier once every MMA issued so far by this thread has completed (implies fence::before_thread_sync).
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

@@ -134,7 +134,7 @@ struct __align__(1024) Tc2Smem {
     int jidx[TC_ROWS];
     uint64_t w_full[T2_NW], w_empty[T2_NW];
     uint64_t act_full[T2_NACT], act_empty[T2_NACT];
-    uint64_t a_ready[4], d_ready[2];
+    uint64_t a_ready[8], d_ready[2];     // a_ready: one per 16-column sub-chunk of the A operand
     uint32_t tmem_base;
 };
 
@@ -175,10 +175,40 @@ __device__ __forceinline__ void halfwarp_colsum32(float (&v)[32], int lane) {
 
 __device__ __forceinline__ void named_bar(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
+// 16 values -> columns [16 sc, 16 sc + 16) of the next A operand (hi plane: the tf32 the tensor core would read anyway;
+// lo plane: the exact remainder, which the tensor core truncates to tf32 itself), then publish the sub-chunk.
+__device__ __forceinline__ void publish_A16(uint32_t lane_addr, int sc, const float (&v)[16], uint64_t* a_ready) {
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        hi[j] = __float_as_uint(v[j]) & 0xffffe000u;
+        lo[j] = __float_as_uint(v[j] - __uint_as_float(hi[j]));
+    }
+    tmem_st16(lane_addr + COL_AHI + sc * 16, hi);
+    tmem_st16(lane_addr + COL_ALO + sc * 16, lo);
+    tmem_wait_st();
+    tc_fence_before();
+    mbar_arrive(a_ready);
+}
+// this thread's 16 floats (columns 16*half ..) of row r of an activation chunk
+__device__ __forceinline__ void load_act16(float (&v)[16], const float* chunk, int r, int half) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float4 t = *reinterpret_cast<const float4*>(chunk + r * ACT_PITCH + half * 16 + j * 4);
+        v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+    }
+}
+__device__ __forceinline__ void load_vec16(float (&v)[16], const float* p) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float4 t = *reinterpret_cast<const float4*>(p + j * 4);
+        v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+    }
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(T2_THREADS, 1) tc_edge_kernel(TcArgs a) {
     constexpr int STAGES = (KIND == TC_UPD) ? 3 : 2;
-    constexpr int ACT_PER_TILE = (KIND == TC_UPD) ? 12 : 8;   // input x4, Q x4, (residual x4)
     extern __shared__ uint8_t smem_raw[];
     Tc2Smem& S = *reinterpret_cast<Tc2Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -187,8 +217,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tc_edge_kernel(TcArgs a) {
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < T2_NW; ++i) { mbar_init(&S.w_full[i], 1); mbar_init(&S.w_empty[i], 1); }
-        for (int i = 0; i < T2_NACT; ++i) { mbar_init(&S.act_full[i], 64); mbar_init(&S.act_empty[i], 128); }
-        for (int i = 0; i < 4; ++i) mbar_init(&S.a_ready[i], 128);
+        for (int i = 0; i < T2_NACT; ++i) { mbar_init(&S.act_full[i], 64); mbar_init(&S.act_empty[i], 256); }
+        for (int i = 0; i < 8; ++i) mbar_init(&S.a_ready[i], 128);
         for (int i = 0; i < 2; ++i) mbar_init(&S.d_ready[i], 1);
         fence_barrier_init();
     }
@@ -215,153 +245,179 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tc_edge_kernel(TcArgs a) {
                 }
         }
     } else if (warp == 8) {
-        // ---------------- MMA issuer ----------------
-        if (lane == 0) {
+        // ---------------- MMA issuer: one 16-column sub-chunk (2 K-steps) at a time, as the epilogue publishes them ----
+        // The whole warp runs the loop so that every operand is warp-uniform (lives in uniform registers); only the
+        // tcgen05 instructions themselves are predicated on lane 0.  Computing operands inside an `if (lane == 0)` region
+        // makes the compiler wrap each UTCHMMA in a ~10-instruction uniform-register "waterfall".
+        {
             const uint32_t idesc = make_idesc_tf32(128, 128);
+            const bool leader = lane == 0;
+            const uint32_t tmem = __shfl_sync(0xffffffffu, S.tmem_base, 0);   // a value the compiler KNOWS is warp-uniform
             uint32_t it = 0, g = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+#pragma unroll 1
                 for (int l = 0; l < STAGES; ++l, ++g) {
                     const uint32_t d = tmem + ((g & 1) ? COL_D1 : COL_D0);
+#pragma unroll 1
                     for (int c = 0; c < 4; ++c, ++it) {
                         const uint32_t sw = it % T2_NW;
-                        mbar_wait(&S.a_ready[c], g & 1);
-                        if (c == 0) TC_STAMP(g / STAGES, 24 + 2 * l);
-                        mbar_wait(&S.w_full[sw], (it / T2_NW) & 1);
-                        tc_fence_after();
-                        const uint32_t bh = smem_u32(S.w[sw]), bl = bh + T2_HALF;
-                        // per K-chunk: the two small correction products first, then hi.hi (the accumulator truncates on
-                        // every add; small terms are best summed among themselves before they meet the large ones)
+                        const uint32_t bh = desc_sw128_lo(smem_u32(S.w[sw]));      // low descriptor word of the B_hi plane
 #pragma unroll
-                        for (int s = 0; s < 4; ++s) {
-                            const uint32_t koff = c * 32 + s * 8;
-                            mma_tf32_ts(d, tmem + COL_ALO + koff, make_desc_sw128(bh + s * 32), idesc, (c | s) != 0);
-                            mma_tf32_ts(d, tmem + COL_AHI + koff, make_desc_sw128(bl + s * 32), idesc, 1);
+                        for (int half = 0; half < 2; ++half) {
+                            const int sc = 2 * c + half;
+                            mbar_wait(&S.a_ready[sc], g & 1);
+                            if (sc == 0) TC_STAMP(g / STAGES, 24 + 2 * l);
+                            if (half == 0) mbar_wait(&S.w_full[sw], (it / T2_NW) & 1);
+                            tc_fence_after();
+                            const uint32_t ahi = tmem + COL_AHI + sc * 16, alo = tmem + COL_ALO + sc * 16;
+                            const bool first = (c == 0) && (half == 0);
+                            // per 16-column sub-chunk: the two small correction products first, then hi.hi; descriptor
+                            // offsets are compile-time (16-byte units: K-step 32 B -> +2, second half +4, lo plane +1024)
+                            if (leader) {
+                                if (first) mma_tf32_ts_lh_init(d, alo, bh, DESC_SW128_HI, idesc);
+                                else mma_tf32_ts_lh(d, alo, bh + half * 4, DESC_SW128_HI, idesc);
+                                mma_tf32_ts_lh(d, ahi, bh + 1024 + half * 4, DESC_SW128_HI, idesc);
+                                mma_tf32_ts_lh(d, alo + 8, bh + half * 4 + 2, DESC_SW128_HI, idesc);
+                                mma_tf32_ts_lh(d, ahi + 8, bh + 1024 + half * 4 + 2, DESC_SW128_HI, idesc);
+                                mma_tf32_ts_lh(d, ahi, bh + half * 4, DESC_SW128_HI, idesc);
+                                mma_tf32_ts_lh(d, ahi + 8, bh + half * 4 + 2, DESC_SW128_HI, idesc);
+                            }
+                            __syncwarp();
                         }
-#pragma unroll
-                        for (int s = 0; s < 4; ++s)
-                            mma_tf32_ts(d, tmem + COL_AHI + c * 32 + s * 8, make_desc_sw128(bh + s * 32), idesc, 1);
-                        mma_commit(&S.w_empty[sw]);
+                        if (leader) mma_commit(&S.w_empty[sw]);
                     }
-                    mma_commit(&S.d_ready[g & 1]);
+                    if (leader) mma_commit(&S.d_ready[g & 1]);
                     TC_STAMP(g / STAGES, 25 + 2 * l);
                 }
         }
     } else if (warp == 10) {
         // ---------------- activation producer ----------------
-        // Every lane owns rows lane, lane+32, lane+64, lane+96 of the tile and copies their 128-byte chunk slices with
+        // Every lane owns rows lane, lane+32, lane+64, lane+96 of a tile and copies their 128-byte chunk slices with
         // eight 16-byte cp.async each (h_E rows, or the neighbour's Q row): no index math inside the copy loop.
         // (One 128-byte bulk copy per row was measured 3x slower: too fine-grained for the TMA unit.)
-        uint32_t ti = 0, k = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+        // Chunk order = the order the epilogue consumes them: in(0) | q(t), in(t+1), [residual(t)] for t = 0, 1, ...
+        uint32_t k = 0;
+        int jrow[4];
+        auto chunk = [&](int row0, int c, bool gather_q, int with_p_buf) {
+            const uint32_t s = k % T2_NACT, u = k / T2_NACT;
+            if (u > 0) mbar_wait(&S.act_empty[s], (u - 1) & 1);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = lane + 32 * i;
+                float* dst = &S.act[s][r * ACT_PITCH];
+                if (gather_q || row0 + r < total_rows) {
+                    const float* src = gather_q ? a.Q + (size_t)jrow[i] * a.q_stride + c * 32
+                                                : a.hE + (size_t)(row0 + r) * HID + c * 32;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) cp_async16_ca(dst + q * 4, src + q * 4);
+                } else {                                   // row past the end of the edge array
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) reinterpret_cast<float4*>(dst)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            if (with_p_buf >= 0) {
+                const int node_lo = row0 / KNB;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    int node = node_lo + i; node = node < N ? node : N - 1;
+                    cp_async16_ca(&S.p[with_p_buf][i][lane * 4], a.P + (size_t)node * a.p_stride + lane * 4);
+                }
+            }
+            cp_async_arrive_noinc(&S.act_full[s]);          // fires when this lane's copies have landed
+            mbar_arrive(&S.act_full[s]);                    // releases this lane's plain stores (zeros, wrow/mrow)
+            ++k;
+        };
+        // metadata of a tile (weights / masks per row) + its four input chunks; returns the neighbour rows in jnext
+        auto tile_input = [&](int tile, uint32_t mb, int (&jnext)[4]) {
             const int row0 = tile * TC_ROWS;
-            const int node_lo = row0 / KNB;
-            const uint32_t mb = ti & 1;
-            int jrow[4];
-            bool okrow[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int r = lane + 32 * i, row = row0 + r;
                 int j = N - 1;
                 float w = 0.f, mi = 0.f;
-                okrow[i] = row < total_rows;
-                if (okrow[i]) {
+                if (row < total_rows) {
                     const int node = row / KNB;
                     mi = a.maskf[node];
                     j = a.E_idx[row];
                     if (j < 0) j = node;                                   // unused slot: a finite dummy
                     else w = (KIND == TC_ENC) ? mi * a.maskf[j] : 1.0f;    // mask_attend (protein_mpnn_utils.py:1232-1233)
                 }
-                jrow[i] = j; S.wrow[mb][r] = w; S.mrow[mb][r] = mi;
+                jnext[i] = j; S.wrow[mb][r] = w; S.mrow[mb][r] = mi;
             }
-            auto chunk = [&](int c, bool gather_q, bool with_p) {
-                const uint32_t s = k % T2_NACT, u = k / T2_NACT;
-                if (u > 0) mbar_wait(&S.act_empty[s], (u - 1) & 1);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int r = lane + 32 * i;
-                    float* dst = &S.act[s][r * ACT_PITCH];
-                    if (gather_q || okrow[i]) {
-                        const float* src = gather_q ? a.Q + (size_t)jrow[i] * a.q_stride + c * 32
-                                                    : a.hE + (size_t)(row0 + r) * HID + c * 32;
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) cp_async16_ca(dst + q * 4, src + q * 4);
-                    } else {                                   // row past the end of the edge array
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) reinterpret_cast<float4*>(dst)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                }
-                if (with_p) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        int node = node_lo + i; node = node < N ? node : N - 1;
-                        cp_async16_ca(&S.p[mb][i][lane * 4], a.P + (size_t)node * a.p_stride + lane * 4);
-                    }
-                }
-                cp_async_arrive_noinc(&S.act_full[s]);          // fires when this lane's copies have landed
-                mbar_arrive(&S.act_full[s]);                    // releases this lane's plain stores (zeros, wrow/mrow)
-                ++k;
-            };
-            for (int c = 0; c < 4; ++c) chunk(c, false, c == 0);
-            for (int c = 0; c < 4; ++c) chunk(c, true, false);
+            for (int c = 0; c < 4; ++c) chunk(row0, c, false, c == 0 ? (int)mb : -1);
+        };
+        uint32_t ti = 0;
+        int tile = blockIdx.x;
+        if (tile < num_tiles) tile_input(tile, 0, jrow);
+        for (; tile < num_tiles; tile += gridDim.x, ++ti) {
+            const int row0 = tile * TC_ROWS;
+            for (int c = 0; c < 4; ++c) chunk(row0, c, true, -1);
+            int jn[4] = {0, 0, 0, 0};
+            const int next = tile + gridDim.x;
+            if (next < num_tiles) tile_input(next, (ti + 1) & 1, jn);
             if (KIND == TC_UPD)
-                for (int c = 0; c < 4; ++c) chunk(c, false, false);
+                for (int c = 0; c < 4; ++c) chunk(row0, c, false, -1);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) jrow[i] = jn[i];
         }
         cp_async_wait<0>();
     } else {
-        // ---------------- epilogue: thread <-> (edge row, chunk parity) ----------------
+        // ---------------- epilogue: thread <-> (edge row, sub-chunk parity) ----------------
         const int set = warp >> 2, quad = warp & 3;
         const int r = quad * 32 + lane;                    // 0..127
         const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
-        uint32_t ti = 0, g = 0;
+        uint32_t ti = 0, g = 0, kc = 0;                    // tile counter, MMA stage counter, activation chunk counter
         auto act_wait = [&](uint32_t k) -> const float* {
             const uint32_t s = k % T2_NACT;
             mbar_wait(&S.act_full[s], (k / T2_NACT) & 1);
             return S.act[s];
         };
         auto act_release = [&](uint32_t k) { mbar_arrive(&S.act_empty[k % T2_NACT]); };
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+        // input stage of a tile: its four h_E chunks -> A (each thread converts its 16-column half of every chunk)
+        auto input_stage = [&]() {
+            for (int c = 0; c < 4; ++c, ++kc) {
+                const float* chunk = act_wait(kc);
+                float v[16];
+                load_act16(v, chunk, r, set);
+                act_release(kc);
+                publish_A16(lane_addr, 2 * c + set, v, &S.a_ready[2 * c + set]);
+            }
+        };
+        int tile = blockIdx.x;
+        const int sb0 = (quad == 0) ? (set ? 16 : 0) : 64;   // only warps 0 and 4 stamp
+#define EPI_STAMP(n_) do { if (sb0 < 32) TC_STAMP(ti, sb0 + (n_)); } while (0)
+        if (tile < num_tiles) input_stage();
+        for (; tile < num_tiles; tile += gridDim.x, ++ti) {
             const int row0 = tile * TC_ROWS;
             const int row = row0 + r;
-            const uint32_t k0 = ti * ACT_PER_TILE, mb = ti & 1;
+            const uint32_t mb = ti & 1;
             int node_l = row / KNB - row0 / KNB;
             node_l = node_l > 3 ? 3 : node_l;
-            const int sb0 = (quad == 0) ? (set ? 16 : 0) : 64;   // only warps 0 and 4 stamp (slot >= 32 is discarded below)
-#define EPI_STAMP(n_) do { if (sb0 < 32) TC_STAMP(ti, sb0 + (n_)); } while (0)
+            const float w_r = S.wrow[mb][r], m_i = S.mrow[mb][r];
             EPI_STAMP(0);
-            // ---- input: h_E rows -> A
-            float w_r = 0.f, m_i = 0.f;
-            for (int c = set; c < 4; c += 2) {
-                const float* slab = act_wait(k0 + c);
-                float v[32];
-                load_act_row(v, slab, r);
-                act_release(k0 + c);
-                publish_A_chunk(lane_addr, c, v, &S.a_ready[c]);
-            }
-            w_r = S.wrow[mb][r];
-            m_i = S.mrow[mb][r];
-            EPI_STAMP(1);
             // ---- stage 1: gathered projections, GELU
             mbar_wait(&S.d_ready[g & 1], (g >> 1) & 1);
             tc_fence_after();
             EPI_STAMP(2);
             {
                 const uint32_t dcol = (g & 1) ? COL_D1 : COL_D0;
-                for (int c = set; c < 4; c += 2) {
-                    uint32_t acc[32];
-                    tmem_ld32(lane_addr + dcol + c * 32, acc);
-                    const float* slab = act_wait(k0 + 4 + c);
-                    float qv[32], v[32];
-                    load_act_row(qv, slab, r);
-                    act_release(k0 + 4 + c);
+                for (int c = 0; c < 4; ++c, ++kc) {
+                    const int sc = 2 * c + set;
+                    uint32_t acc[16];
+                    tmem_ld16(lane_addr + dcol + sc * 16, acc);
+                    const float* chunk = act_wait(kc);
+                    float qv[16], pv[16], v[16];
+                    load_act16(qv, chunk, r, set);
+                    act_release(kc);
+                    load_vec16(pv, &S.p[mb][node_l][sc * 16]);
                     tmem_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float pj = S.p[mb][node_l][c * 32 + j];
-                        const float pre = (KIND == TC_DEC) ? fmaf(m_i, __uint_as_float(acc[j]) + qv[j], pj)
-                                                           : (__uint_as_float(acc[j]) + pj + qv[j]);
+                    for (int j = 0; j < 16; ++j) {
+                        const float pre = (KIND == TC_DEC) ? fmaf(m_i, __uint_as_float(acc[j]) + qv[j], pv[j])
+                                                           : (__uint_as_float(acc[j]) + pv[j] + qv[j]);
                         v[j] = gelu_fast(pre);
                     }
-                    publish_A_chunk(lane_addr, c, v, &S.a_ready[c]);
+                    publish_A16(lane_addr, sc, v, &S.a_ready[sc]);
                 }
             }
             ++g;
@@ -373,106 +429,128 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tc_edge_kernel(TcArgs a) {
                 EPI_STAMP(4);
                 {
                     const uint32_t dcol = (g & 1) ? COL_D1 : COL_D0;
-                    for (int c = set; c < 4; c += 2) {
-                        uint32_t acc[32];
-                        tmem_ld32(lane_addr + dcol + c * 32, acc);
+                    for (int c = 0; c < 4; ++c) {
+                        const int sc = 2 * c + set;
+                        uint32_t acc[16];
+                        tmem_ld16(lane_addr + dcol + sc * 16, acc);
+                        float bv[16], v[16];
+                        load_vec16(bv, &S.vec[0][sc * 16]);
                         tmem_wait_ld();
-                        float v[32];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = gelu_fast(__uint_as_float(acc[j]) + S.vec[0][c * 32 + j]);
-                        publish_A_chunk(lane_addr, c, v, &S.a_ready[c]);
+                        for (int j = 0; j < 16; ++j) v[j] = gelu_fast(__uint_as_float(acc[j]) + bv[j]);
+                        publish_A16(lane_addr, sc, v, &S.a_ready[sc]);
                     }
                 }
                 ++g;
                 EPI_STAMP(5);
-                // ---- stage 3: + b13 + residual, LayerNorm over the row (two threads per row), coalesced write-back
-                mbar_wait(&S.d_ready[g & 1], (g >> 1) & 1);
-                tc_fence_after();
-                EPI_STAMP(6);
-                {
-                    const uint32_t dcol = (g & 1) ? COL_D1 : COL_D0;
-                    float shift = 0.f, s1 = 0.f, s2 = 0.f;
-                    for (int c = set; c < 4; c += 2) {
-                        uint32_t acc[32];
-                        tmem_ld32(lane_addr + dcol + c * 32, acc);
-                        const float* slab = act_wait(k0 + 8 + c);
-                        float old[32];
-                        load_act_row(old, slab, r);
-                        act_release(k0 + 8 + c);
-                        tmem_wait_ld();
-                        if (c == set) shift = __uint_as_float(acc[0]) + S.vec[1][c * 32] + old[0];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float x = __uint_as_float(acc[j]) + S.vec[1][c * 32 + j] + old[j];
-                            acc[j] = __float_as_uint(x);
-                            const float dlt = x - shift;
-                            s1 += dlt;
-                            s2 = fmaf(dlt, dlt, s2);
-                        }
-                        tmem_st32(lane_addr + dcol + c * 32, acc);
-                    }
-                    tmem_wait_st();
-                    // this thread's 64 values: mean_a, M2_a; combine with the partner's (Chan et al.)
-                    const float mean_a = shift + s1 * (1.0f / 64.0f);
-                    const float m2_a = fmaxf(s2 - s1 * s1 * (1.0f / 64.0f), 0.f);
-                    S.lnx[set][r] = make_float2(mean_a, m2_a);
-                    named_bar(3, 256);
-                    const float2 ob = S.lnx[set ^ 1][r];
-                    const float dm = mean_a - ob.x;
-                    const float mean = 0.5f * (mean_a + ob.x);
-                    const float var = (m2_a + ob.y + 32.0f * dm * dm) * (1.0f / HID);
-                    const float rstd = 1.0f / sqrtf(var + LN_EPS);
-                    for (int c = set; c < 4; c += 2) {
-                        uint32_t xv[32];
-                        tmem_ld32(lane_addr + dcol + c * 32, xv);
-                        tmem_wait_ld();
-                        float o[32];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            o[j] = (__uint_as_float(xv[j]) - mean) * rstd * S.vec[2][c * 32 + j] + S.vec[3][c * 32 + j];
-                        store_row_chunk(S.out[set], r, o);
-                        named_bar(1 + set, 128);
-                        for (int i = 0; i < 8; ++i) {                       // 128 rows x 128 B, coalesced
-                            const int idx = i * 128 + r, rr = idx >> 3, ch = idx & 7;
-                            if (row0 + rr < total_rows)
-                                *reinterpret_cast<float4*>(a.hE + (size_t)(row0 + rr) * HID + c * 32 + ch * 4) =
-                                    *reinterpret_cast<const float4*>(&S.out[set][slab_off(rr, ch)]);
-                        }
-                        named_bar(1 + set, 128);
-                    }
-                }
-                ++g;
-                tc_fence_before();
-                EPI_STAMP(7);
-            } else {
-                // ---- stage 2 (final): + b2, GELU, weight, per-residue column sums of each 16-row half-warp
-                mbar_wait(&S.d_ready[g & 1], (g >> 1) & 1);
-                tc_fence_after();
-                EPI_STAMP(4);
-                {
-                    const uint32_t dcol = (g & 1) ? COL_D1 : COL_D0;
-                    const int sb = (row0 + quad * 32) / 16 + (lane >> 4);   // 16-row sub-block of the edge array
-                    const int node = sb / 3, part = sb - node * 3;
-                    for (int c = set; c < 4; c += 2) {
-                        uint32_t acc[32];
-                        tmem_ld32(lane_addr + dcol + c * 32, acc);
-                        tmem_wait_ld();
-                        float gv[32];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float gl = gelu_fast(__uint_as_float(acc[j]) + S.vec[0][c * 32 + j]);
-                            gv[j] = (w_r != 0.f) ? w_r * gl : 0.f;
-                        }
-                        halfwarp_colsum32(gv, lane);
-                        if (node < N)
-                            *reinterpret_cast<float2*>(a.Spart + ((size_t)node * 3 + part) * HID + c * 32 + 2 * (lane & 15)) =
-                                make_float2(gv[0], gv[1]);
-                    }
-                }
-                ++g;
-                tc_fence_before();
-                EPI_STAMP(7);
             }
+            // ---- last GEMM of this tile done -> A is free: feed the NEXT tile's input so its first GEMM runs under our final stage
+            mbar_wait(&S.d_ready[g & 1], (g >> 1) & 1);
+            tc_fence_after();
+            EPI_STAMP(KIND == TC_UPD ? 6 : 4);
+            const uint32_t dcol = (g & 1) ? COL_D1 : COL_D0;
+            ++g;
+            if (tile + (int)gridDim.x < num_tiles) input_stage();
+            EPI_STAMP(1);
+            if (KIND == TC_UPD) {
+                // ---- final: + b13 + residual, LayerNorm over the row (two threads per row), direct 64-byte row stores
+                float shift = 0.f, s1 = 0.f, s2 = 0.f;
+                for (int c = 0; c < 4; ++c, ++kc) {
+                    const int sc = 2 * c + set;
+                    uint32_t acc[16];
+                    tmem_ld16(lane_addr + dcol + sc * 16, acc);
+                    const float* chunk = act_wait(kc);
+                    float old[16], bv[16];
+                    load_act16(old, chunk, r, set);
+                    act_release(kc);
+                    load_vec16(bv, &S.vec[1][sc * 16]);
+                    tmem_wait_ld();
+                    if (c == 0) shift = __uint_as_float(acc[0]) + bv[0] + old[0];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float x = __uint_as_float(acc[j]) + bv[j] + old[j];
+                        acc[j] = __float_as_uint(x);
+                        const float dlt = x - shift;
+                        s1 += dlt;
+                        s2 = fmaf(dlt, dlt, s2);
+                    }
+                    tmem_st16(lane_addr + dcol + sc * 16, acc);
+                }
+                tmem_wait_st();
+                // this thread's 64 values: mean_a, M2_a; combine with the partner's (Chan et al.)
+                const float mean_a = shift + s1 * (1.0f / 64.0f);
+                const float m2_a = fmaxf(s2 - s1 * s1 * (1.0f / 64.0f), 0.f);
+                S.lnx[set][r] = make_float2(mean_a, m2_a);
+                named_bar(3, 256);
+                const float2 ob = S.lnx[set ^ 1][r];
+                const float dm = mean_a - ob.x;
+                const float mean = 0.5f * (mean_a + ob.x);
+                const float var = (m2_a + ob.y + 32.0f * dm * dm) * (1.0f / HID);
+                const float rstd = 1.0f / sqrtf(var + LN_EPS);
+                float* ost = &S.out[0][0];                      // [128 rows][64 cols], 16-byte chunks XOR-swizzled by row
+                for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc) {
+                        const int sc = 4 * hf + 2 * cc + set;       // this thread's two sub-chunks of the half
+                        uint32_t xv[16];
+                        tmem_ld16(lane_addr + dcol + sc * 16, xv);
+                        float gv[16], bv[16];
+                        load_vec16(gv, &S.vec[2][sc * 16]);
+                        load_vec16(bv, &S.vec[3][sc * 16]);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int ch = (sc & 3) * 4 + j;            // 16-byte chunk 0..15 inside the 64-column half
+                            *reinterpret_cast<float4*>(ost + r * 64 + ((ch ^ (r & 15)) << 2)) =
+                                make_float4((__uint_as_float(xv[4 * j]) - mean) * rstd * gv[4 * j] + bv[4 * j],
+                                            (__uint_as_float(xv[4 * j + 1]) - mean) * rstd * gv[4 * j + 1] + bv[4 * j + 1],
+                                            (__uint_as_float(xv[4 * j + 2]) - mean) * rstd * gv[4 * j + 2] + bv[4 * j + 2],
+                                            (__uint_as_float(xv[4 * j + 3]) - mean) * rstd * gv[4 * j + 3] + bv[4 * j + 3]);
+                        }
+                    }
+                    named_bar(3, 256);
+                    {   // 128 rows x 256 B: 16 lanes per row, 8 passes
+                        const int t = set * 128 + r;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int idx = i * 256 + t, rr = idx >> 4, ch = idx & 15;
+                            if (row0 + rr < total_rows)
+                                *reinterpret_cast<float4*>(a.hE + (size_t)(row0 + rr) * HID + hf * 64 + ch * 4) =
+                                    *reinterpret_cast<const float4*>(ost + rr * 64 + ((ch ^ (rr & 15)) << 2));
+                        }
+                    }
+                    named_bar(3, 256);
+                }
+            } else {
+                // ---- final: + b2, GELU, weight, per-residue column sums of each 16-row half-warp
+                const int sb = (row0 + quad * 32) / 16 + (lane >> 4);   // 16-row sub-block of the edge array
+                const int node = sb / 3, part = sb - node * 3;
+                for (int c = 0; c < 4; c += 2) {                       // two 16-column sub-chunks per transpose-reduce
+                    float gv[32];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int sc = 2 * (c + h) + set;
+                        uint32_t acc[16];
+                        tmem_ld16(lane_addr + dcol + sc * 16, acc);
+                        float bv[16];
+                        load_vec16(bv, &S.vec[0][sc * 16]);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float gl = gelu_fast(__uint_as_float(acc[j]) + bv[j]);
+                            gv[h * 16 + j] = (w_r != 0.f) ? w_r * gl : 0.f;
+                        }
+                    }
+                    halfwarp_colsum32(gv, lane);       // lane l: local columns 2(l&15), 2(l&15)+1 of the 32 gathered above
+                    if (node < N) {
+                        const int lc = 2 * (lane & 15), h = lc >> 4;             // which of the two sub-chunks, column inside it
+                        const int col = (2 * (c + h) + set) * 16 + (lc & 15);
+                        *reinterpret_cast<float2*>(a.Spart + ((size_t)node * 3 + part) * HID + col) = make_float2(gv[0], gv[1]);
+                    }
+                }
+            }
+            tc_fence_before();
+            EPI_STAMP(7);
         }
     }
     __syncwarp();
@@ -559,32 +637,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_feat_kernel(TcFeatArgs 
                 }
         }
     } else if (warp == 4) {
-        if (lane == 0) {                                  // MMA issuer
+        {                                                 // MMA issuer (whole warp runs the loop; lane 0 issues)
+            // GEMM1 (416 deep): hi.hi products accumulate in D0, the small corrections (lo.hi, hi.lo) in D1 -- with 13
+            // K-chunks the truncating accumulator would otherwise lose them against the large partial sums (this GEMM was
+            // the whole end-to-end error of the tensor-core path).  The epilogue adds D0 + D1.  GEMM2 (W_e) -> D1.
             const uint32_t idesc = make_idesc_tf32(128, 128);
-            uint32_t it = 0, g = 0, acnt[4] = {0, 0, 0, 0};
+            const bool leader = lane == 0;
+            const uint32_t tmem = __shfl_sync(0xffffffffu, S.tmem_base, 0);   // warp-uniform for the compiler
+            uint32_t it = 0, apar = 0;                        // apar: bit s = parity of a_ready[s]'s next completion
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
-                for (int l = 0; l < 2; ++l, ++g) {
-                    const uint32_t d = tmem + ((g & 1) ? COL_D1 : COL_D0);
+#pragma unroll 1
+                for (int l = 0; l < 2; ++l) {
                     const int nch = l == 0 ? K1_CHUNKS : 4;
+                    const uint32_t d_main = tmem + (l == 0 ? COL_D0 : COL_D1), d_corr = tmem + COL_D1;
+#pragma unroll 1
                     for (int c = 0; c < nch; ++c, ++it) {
                         const uint32_t slot = it % TC_WSLOTS, as = c & 3;
-                        mbar_wait(&S.a_ready[as], acnt[as] & 1);
-                        ++acnt[as];
+                        mbar_wait(&S.a_ready[as], (apar >> as) & 1);
+                        apar ^= 1u << as;
                         mbar_wait(&S.w_full[slot], (it / TC_WSLOTS) & 1);
                         tc_fence_after();
-                        const uint32_t wb = smem_u32(S.wring[slot]);
+                        const uint32_t bh = desc_sw128_lo(smem_u32(S.wring[slot]));
+                        const uint32_t ahi = tmem + COL_AHI + as * 32, alo = tmem + COL_ALO + as * 32;
+                        if (leader) {
+                            if (c == 0) mma_tf32_ts_lh_init(d_corr, alo, bh, DESC_SW128_HI, idesc);
+                            else mma_tf32_ts_lh(d_corr, alo, bh, DESC_SW128_HI, idesc);
+                            mma_tf32_ts_lh(d_corr, ahi, bh + 1024, DESC_SW128_HI, idesc);
 #pragma unroll
-                        for (int s = 0; s < 4; ++s) {
-                            const uint32_t koff = as * 32 + s * 8;
-                            const uint64_t bh = make_desc_sw128(wb + s * 32), bl = make_desc_sw128(wb + 16384 + s * 32);
-                            mma_tf32_ts(d, tmem + COL_AHI + koff, bh, idesc, (c | s) != 0);
-                            mma_tf32_ts(d, tmem + COL_ALO + koff, bh, idesc, 1);
-                            mma_tf32_ts(d, tmem + COL_AHI + koff, bl, idesc, 1);
+                            for (int s = 1; s < 4; ++s) {
+                                mma_tf32_ts_lh(d_corr, alo + s * 8, bh + s * 2, DESC_SW128_HI, idesc);
+                                mma_tf32_ts_lh(d_corr, ahi + s * 8, bh + 1024 + s * 2, DESC_SW128_HI, idesc);
+                            }
+                            if (l == 0 && c == 0) mma_tf32_ts_lh_init(d_main, ahi, bh, DESC_SW128_HI, idesc);
+                            else mma_tf32_ts_lh(d_main, ahi, bh, DESC_SW128_HI, idesc);
+#pragma unroll
+                            for (int s = 1; s < 4; ++s) mma_tf32_ts_lh(d_main, ahi + s * 8, bh + s * 2, DESC_SW128_HI, idesc);
+                            mma_commit(&S.w_empty[slot]);
+                            mma_commit(&S.a_free[as]);
                         }
-                        mma_commit(&S.w_empty[slot]);
-                        mma_commit(&S.a_free[as]);
-                        if (c == nch - 1) mma_commit(&S.d_ready[g & 1]);
+                        __syncwarp();
                     }
+                    if (leader) mma_commit(&S.d_ready[l]);
                 }
         }
     } else if (warp == 6) {
@@ -622,10 +715,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_feat_kernel(TcFeatArgs 
     } else {
         const int r = threadIdx.x;
         const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
-        uint32_t ti = 0, g = 0, pub[4] = {0, 0, 0, 0};
+        uint32_t ti = 0, pub = 0;      // pub: bit s = parity of a_free[s]'s next completion, bit 8+s = slot s used before
         auto publish = [&](int slot, const float (&v)[32]) {
-            if (pub[slot] > 0) mbar_wait(&S.a_free[slot], (pub[slot] - 1) & 1);   // the MMAs that read this slot are done
-            ++pub[slot];
+            if ((pub >> (8 + slot)) & 1) {                       // wait until the MMAs that read this slot are done
+                mbar_wait(&S.a_free[slot], (pub >> slot) & 1);
+                pub ^= 1u << slot;
+            }
+            pub |= 1u << (8 + slot);
             tc_fence_after();
             publish_A_chunk(lane_addr, slot, v, &S.a_ready[slot]);
         };
@@ -668,30 +764,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_feat_kernel(TcFeatArgs 
             }
             mbar_arrive(&S.in_empty);
             // ---- norm_edges (thread-local LayerNorm over the 128 accumulator columns) -> A of the W_e GEMM
-            mbar_wait(&S.d_ready[g & 1], (g >> 1) & 1);
+            mbar_wait(&S.d_ready[0], ti & 1);
             tc_fence_after();
             {
-                const uint32_t dcol = (g & 1) ? COL_D1 : COL_D0;
                 float shift = 0.f, s1 = 0.f, s2 = 0.f;
                 for (int c = 0; c < 4; ++c) {
-                    uint32_t acc[32];
-                    tmem_ld32(lane_addr + dcol + c * 32, acc);
+                    uint32_t acc[32], cor[32];
+                    tmem_ld32(lane_addr + COL_D0 + c * 32, acc);
+                    tmem_ld32(lane_addr + COL_D1 + c * 32, cor);
                     tmem_wait_ld();
-                    if (c == 0) shift = __uint_as_float(acc[0]);
+                    if (c == 0) shift = __uint_as_float(acc[0]) + __uint_as_float(cor[0]);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const float dlt = __uint_as_float(acc[j]) - shift;
+                        const float x = __uint_as_float(acc[j]) + __uint_as_float(cor[j]);
+                        acc[j] = __float_as_uint(x);
+                        const float dlt = x - shift;
                         s1 += dlt;
                         s2 = fmaf(dlt, dlt, s2);
                     }
+                    tmem_st32(lane_addr + COL_D0 + c * 32, acc);
                 }
+                tmem_wait_st();
+                tc_fence_before();
+                epi_bar_sync();          // every row has finished reading D1: the W_e GEMM may overwrite it
+                tc_fence_after();
                 const float ms = s1 * (1.0f / HID);
                 const float mean = shift + ms;
                 const float var = fmaxf(s2 * (1.0f / HID) - ms * ms, 0.f);
                 const float rstd = 1.0f / sqrtf(var + LN_EPS);
                 for (int c = 0; c < 4; ++c) {
                     uint32_t acc[32];
-                    tmem_ld32(lane_addr + dcol + c * 32, acc);
+                    tmem_ld32(lane_addr + COL_D0 + c * 32, acc);
                     tmem_wait_ld();
                     float v[32];
 #pragma unroll
@@ -700,15 +803,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_feat_kernel(TcFeatArgs 
                     publish(c, v);
                 }
             }
-            ++g;
             // ---- W_e output + bias -> staging -> coalesced store
-            mbar_wait(&S.d_ready[g & 1], (g >> 1) & 1);
+            mbar_wait(&S.d_ready[1], ti & 1);
             tc_fence_after();
             {
-                const uint32_t dcol = (g & 1) ? COL_D1 : COL_D0;
                 for (int c = 0; c < 4; ++c) {
                     uint32_t acc[32];
-                    tmem_ld32(lane_addr + dcol + c * 32, acc);
+                    tmem_ld32(lane_addr + COL_D1 + c * 32, acc);
                     tmem_wait_ld();
                     float o[32];
 #pragma unroll
@@ -716,7 +817,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_feat_kernel(TcFeatArgs 
                     store_row_chunk(S.out[c], r, o);
                 }
             }
-            ++g;
             tc_fence_before();
             epi_bar_sync();
             for (int i = 0; i < 32; ++i) {

@@ -12,7 +12,7 @@ eng = model._get_engine()
 p = featurize_batch(config3(32))
 for _ in range(2): eng.run(p.offsets, p.X, p.S, p.residue_idx, p.chain_enc, p.mask)
 tr = eng.fetch_trace()
-names_e = {0: "start", 1: "input done", 2: "d1 seen", 3: "st1 epi done", 4: "d2 seen", 5: "st2 epi done", 6: "d3 seen", 7: "tile done"}
+names_e = {0: "start(st1)", 1: "next input done", 2: "d1 seen", 3: "st1 epi done", 4: "d2 seen", 5: "st2 epi done", 6: "d3 seen", 7: "tile done"}
 for kname, t in (("enc_msg (layer 1)", tr[0]), ("edge_upd (layer 1)", tr[1])):
     print("====", kname, " (cycles; ~1.9 cycles/ns)")
     for ti in range(2, 6):
