@@ -150,21 +150,36 @@ struct Prep {
         return off;
     }
     LayerNormW ln(const std::string& p) { return {vec(p + ".weight"), vec(p + ".bias")}; }
-    // projections: (weight name, first input column) pairs appended to the layer's stream
+    // One 16 KB chunk [32 k][128 n] of nn.Linear W[out][in]:  chunk[k][n] = W[out0 + n][in0 + k]  (zero outside the matrix)
+    int64_t put_chunk(int64_t off, const std::string& name, int out0, int in0) {
+        int out, in;
+        const float* W = find(name, &out, &in);
+        for (int k = 0; k < 32; ++k)
+            for (int n = 0; n < HID; ++n)
+                dev[off + (int64_t)k * HID + n] = (out0 + n < out && in0 + k < in) ? W[(int64_t)(out0 + n) * in + in0 + k] : 0.f;
+        return 4096;
+    }
+    // node_update weights in STEP order (four chunks per step, one per thread group q; node_kernels.cu):
+    //   W3 (K split: group q = rows 32q..)  |  W_in: step s = rows 32s.. of column block q  |
+    //   W_out (K split: group q = rows (4q+s)*32..)  |  projections: step s = rows 32s.. of projection q
+    //   (two projections: group q = projection q&1, K half q>>1, two steps)
     NodeUpdW node_upd(const std::string& p, const std::vector<std::pair<std::string, int>>& projs) {
         NodeUpdW w;
-        w.nchunks = 4 + 16 + 16 + 4 * (int)projs.size();
+        // projections: step s = rows 32s.. of projection q (zero chunks pad q >= number of projections)
+        const int pchunks = projs.empty() ? 0 : 16;
+        w.nchunks = 4 * (1 + 4 + 4) + pchunks;
         w.stream = alloc((int64_t)w.nchunks * 4096);
         int64_t o = w.stream;
-        put_kn(o, p + "W3.weight", 0, HID); o += HID * HID;
-        {   // W_in [512][128] -> four [128 k][128 n] column blocks
-            const float* W = find(p + "dense.W_in.weight");
-            for (int blk = 0; blk < 4; ++blk, o += HID * HID)
-                for (int k = 0; k < HID; ++k)
-                    for (int n = 0; n < HID; ++n) dev[o + (int64_t)k * HID + n] = W[(int64_t)(blk * HID + n) * HID + k];
-        }
-        put_kn(o, p + "dense.W_out.weight", 0, 4 * HID); o += 4 * HID * HID;
-        for (auto& pr : projs) { put_kn(o, pr.first, pr.second, HID); o += HID * HID; }
+        for (int q = 0; q < 4; ++q) o += put_chunk(o, p + "W3.weight", 0, 32 * q);
+        for (int s = 0; s < 4; ++s)
+            for (int q = 0; q < 4; ++q) o += put_chunk(o, p + "dense.W_in.weight", HID * q, 32 * s);
+        for (int s = 0; s < 4; ++s)
+            for (int q = 0; q < 4; ++q) o += put_chunk(o, p + "dense.W_out.weight", 0, (4 * q + s) * 32);
+        for (int s = 0; s < (pchunks ? 4 : 0); ++s)
+            for (int q = 0; q < 4; ++q) {
+                if (q < (int)projs.size()) put_chunk(o, projs[q].first, 0, projs[q].second + 32 * s);
+                o += 4096;   // (alloc() zero-fills)
+            }
         w.b3 = vec(p + "W3.bias");
         w.n1 = ln(p + "norm1");
         w.n2 = ln(p + "norm2");
@@ -301,14 +316,17 @@ DevLayout prepare_weights(Prep& P) {
         }
     }
     L.Ws = P.vec(pm + "W_s.weight");
-    {
-        L.head = P.alloc((int64_t)51 * 4096);
+    {   // head weights in step order (14 steps, all K-split: group q = rows (q*steps + s)*32.. of the phase's matrix)
+        L.head = P.alloc((int64_t)56 * 4096);
         int64_t o = L.head;
         for (int blk = 0; blk < 3; ++blk)
-            o += P.put_kn_padded(o, "light_attention.feature_convolution.weight_center", 0, blk * HID, 3 * HID);
-        o += P.put_kn_padded(o, "both_out.1.weight", 0, 0, 3 * HID);
-        o += P.put_kn_padded(o, "both_out.3.weight", 0, 0, 64);
-        o += P.put_kn_padded(o, "both_out.5.weight", 0, 0, 32);
+            for (int s = 0; s < 3; ++s)
+                for (int q = 0; q < 4; ++q)
+                    o += P.put_chunk(o, "light_attention.feature_convolution.weight_center", blk * HID, (3 * q + s) * 32);
+        for (int s = 0; s < 3; ++s)
+            for (int q = 0; q < 4; ++q) o += P.put_chunk(o, "both_out.1.weight", 0, (3 * q + s) * 32);
+        for (int q = 0; q < 4; ++q) o += P.put_chunk(o, "both_out.3.weight", 0, 32 * q);
+        for (int q = 0; q < 4; ++q) o += P.put_chunk(o, "both_out.5.weight", 0, 32 * q);
     }
     L.la_b = P.vec("light_attention.feature_convolution.bias");
     L.m1_b = P.vec("both_out.1.bias");

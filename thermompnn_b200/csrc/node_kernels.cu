@@ -1,84 +1,104 @@
 // Per-residue kernels: node_update (tail of every Enc/Dec layer) and head.
 //
-// These are skinny GEMMs (a few residues x 128..512 x 128) over ~0.8 MB of weights per
-// call, so they are bound by how fast one SM can pull weights out of L2, not by FMAs.
-// Each block therefore keeps SEVEN 16 KB weight chunks in flight through an 8-slot
-// shared-memory ring (cp.async), and 512 threads split every 32-row chunk four ways
-// along k (kq = tid/128 owns 8 rows, n = tid%128 owns one output column).
+// These are skinny GEMM chains (a few residues x 128..512 x 128) over ~0.8 MB of weights per call: latency- and
+// L2->SM-stream-bound, not FLOP-bound.  A block has 512 threads = four groups of 128 (q = tid/128, n = tid%128 = output
+// column).  Work proceeds in STEPS of four 16 KB weight chunks ([32 k][128 n]) -- one chunk per group -- so that the
+// groups run four different matrices (FFN column blocks, projections) or four K-slices of one matrix (W3, W_out) side
+// by side: 13 steps per call instead of 52 sequential chunks.  The next step's 64 KB is prefetched (cp.async) under the
+// current step; one block barrier per step.  The host lays the weights out step-major, group-minor (engine.cu).
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
 namespace tmpnn {
 
 constexpr int NK_THREADS = 512;
-constexpr int NK_RING = 8;
-constexpr int NK_DIST = NK_RING - 1;
+constexpr int STEP_FLOATS = 4 * WCHUNK_FLOATS;   // four chunks = 64 KB
 
-struct NodeStream {
+struct StepStream {
     const float* base;
-    float* ring;
-    int total;
-    __device__ __forceinline__ void issue(int g) {
-        if (g < total) {
-            const float* src = base + (size_t)g * WCHUNK_FLOATS;
-            float* dst = ring + (g % NK_RING) * WCHUNK_FLOATS;
+    float* ring;      // 2 x STEP_FLOATS
+    int total, s;
+    __device__ __forceinline__ void issue(int step) {
+        if (step < total) {
+            const float* src = base + (size_t)step * STEP_FLOATS;
+            float* dst = ring + (step & 1) * STEP_FLOATS;
 #pragma unroll
-            for (int i = 0; i < WCHUNK_FLOATS / 4 / NK_THREADS; ++i) {
-                int e = (threadIdx.x + i * NK_THREADS) * 4;
+            for (int i = 0; i < STEP_FLOATS / 4 / NK_THREADS; ++i) {
+                const int e = (threadIdx.x + i * NK_THREADS) * 4;
                 cp_async16(dst + e, src + e);
             }
         }
         cp_async_commit();
     }
     __device__ __forceinline__ void start(const float* b, float* r, int t) {
-        base = b; ring = r; total = t;
-#pragma unroll
-        for (int g = 0; g < NK_DIST; ++g) issue(g);
+        base = b; ring = r; total = t; s = 0;
+        issue(0);
     }
-    __device__ __forceinline__ const float* get(int g) {
-        cp_async_wait<NK_DIST - 1>();
-        __syncthreads();
-        issue(g + NK_DIST);
-        return ring + (g % NK_RING) * WCHUNK_FLOATS;
+    // Block-wide.  Returns this step's four chunks; publishes every shared-memory write made before the call.
+    __device__ __forceinline__ const float* next() {
+        cp_async_wait<0>();
+        __syncthreads();          // step s has landed; everyone is done with step s-1 (whose half is reused below)
+        issue(s + 1);
+        const float* p = ring + (s & 1) * STEP_FLOATS;
+        ++s;
+        return p;
     }
 };
 
-// res[j] (residue t = kq + 4j, column n) = sum_k xin[t][k] * W[k][n] over the next `nchunks` chunks.
+// acc[t] += sum_{kk<32} x[t][kk] * W[kk][n]      (x: this group's 32-column slice of the input rows)
 template <int NT>
-__device__ __forceinline__ void node_phase(float (&res)[NT / 4], NodeStream& ws, int& g, int nchunks,
-                                           const float* xin, int ldx, float* part) {
-    const int kq = threadIdx.x >> 7, n = threadIdx.x & 127;
+__device__ __forceinline__ void step_fma(float (&acc)[NT], const float* __restrict__ W, const float* __restrict__ x, int ldx, int n) {
+#pragma unroll
+    for (int kk = 0; kk < WCHUNK_K; kk += 4) {
+        const float w0 = W[kk * HID + n], w1 = W[(kk + 1) * HID + n], w2 = W[(kk + 2) * HID + n], w3 = W[(kk + 3) * HID + n];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const float4 xv = *reinterpret_cast<const float4*>(x + t * ldx + kk);
+            acc[t] = fmaf(xv.x, w0, acc[t]);
+            acc[t] = fmaf(xv.y, w1, acc[t]);
+            acc[t] = fmaf(xv.z, w2, acc[t]);
+            acc[t] = fmaf(xv.w, w3, acc[t]);
+        }
+    }
+}
+
+// One matrix, K split four ways: group q takes rows [(q*steps + s)*32, +32) in step s.  Result: res[j] for residue
+// t = q + 4j, column n (the four partials are added in a fixed order).
+template <int NT>
+__device__ __forceinline__ void phase_ksplit(float (&res)[NT / 4], StepStream& ws, int steps, const float* xin, int ldx, float* part) {
+    const int q = threadIdx.x >> 7, n = threadIdx.x & 127;
     float acc[NT];
 #pragma unroll
     for (int t = 0; t < NT; ++t) acc[t] = 0.f;
-    for (int c = 0; c < nchunks; ++c) {
-        const float* W = ws.get(g++);
-        const float* wp = W + (kq * 8) * HID + n;
-        const float* xp = xin + c * WCHUNK_K + kq * 8;
-#pragma unroll
-        for (int kk = 0; kk < 8; kk += 4) {
-            float w0 = wp[kk * HID], w1 = wp[(kk + 1) * HID], w2 = wp[(kk + 2) * HID], w3 = wp[(kk + 3) * HID];
-#pragma unroll
-            for (int t = 0; t < NT; ++t) {
-                float4 xv = *reinterpret_cast<const float4*>(xp + t * ldx + kk);
-                acc[t] = fmaf(xv.x, w0, acc[t]);
-                acc[t] = fmaf(xv.y, w1, acc[t]);
-                acc[t] = fmaf(xv.z, w2, acc[t]);
-                acc[t] = fmaf(xv.w, w3, acc[t]);
-            }
-        }
+    for (int s = 0; s < steps; ++s) {
+        const float* W = ws.next() + q * WCHUNK_FLOATS;
+        step_fma<NT>(acc, W, xin + (q * steps + s) * WCHUNK_K, ldx, n);
     }
 #pragma unroll
-    for (int t = 0; t < NT; ++t) part[(kq * NT + t) * HID + n] = acc[t];
+    for (int t = 0; t < NT; ++t) part[(q * NT + t) * HID + n] = acc[t];
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < NT / 4; ++j) {
-        int t = kq + 4 * j;
+        const int t = q + 4 * j;
         res[j] = (part[t * HID + n] + part[(NT + t) * HID + n]) + (part[(2 * NT + t) * HID + n] + part[(3 * NT + t) * HID + n]);
     }
 }
 
-// LayerNorm over the 128 columns held by the four warps that share kq.  Block-wide barriers inside.
+// Four matrices side by side (K = 128 each, four steps): group q computes matrix q for all NT residues.
+template <int NT>
+__device__ __forceinline__ void phase_4mat(float (&acc)[NT], StepStream& ws, const float* xin, int ldx) {
+    const int q = threadIdx.x >> 7, n = threadIdx.x & 127;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) acc[t] = 0.f;
+    for (int s = 0; s < 4; ++s) {
+        const float* W = ws.next() + q * WCHUNK_FLOATS;
+        step_fma<NT>(acc, W, xin + s * WCHUNK_K, ldx, n);
+    }
+}
+
+// LayerNorm over the 128 columns held by the four warps of a group.  Block-wide barriers inside.
 template <int NJ>
 __device__ __forceinline__ void group_layernorm(float (&v)[NJ], const float* __restrict__ g, const float* __restrict__ b,
                                                 float* red /*[16][NJ]*/) {
@@ -117,25 +137,210 @@ __device__ __forceinline__ void group_layernorm(float (&v)[NJ], const float* __r
 // ---------------------------------------------------------------------------
 // node_update:  dh = (W3.Ssum + cnt*b3)/30 ; h = LN1(h_V + dh) ; h = LN2(h + FFN(h)) ; h *= mask
 // (protein_mpnn_utils.py:826-832, 871-880), then the projections the next kernels gather.
-// Stream order: W3 | W_in column blocks 0..3 | W_out | projections.
+//
+// A tile of NT residues is handled by a CLUSTER of four CTAs.  CTA q streams only chunk q of every step (a quarter of
+// the 0.8 MB), through a 6-deep cp.async ring:
+//   W3      K-split   CTA q: input columns [32q, 32q+32)            -> partial [NT][128]  -> cluster all-reduce
+//   W_in    4 mats    CTA q: hidden block q (columns [128q, 128q+128))                    -> stays local ...
+//   W_out   K-split   CTA q: rows [128q, 128q+128) = exactly the hidden block it produced -> partial -> all-reduce
+//   proj    4 mats    CTA q: projection q (with two projections CTAs 0,1 take one each)
+// The two all-reduces exchange [NT][128] partials through distributed shared memory and add them in rank order, so
+// the result does not depend on timing.  LayerNorms are computed redundantly by the four CTAs.
+// Inside a CTA, thread (kq = tid/128, n = tid%128) takes rows [8kq, 8kq+8) of the 32-row chunk and column n.
+// ---------------------------------------------------------------------------
+constexpr int NC_RING = 6;
+constexpr int NC_THREADS = 512;
+
+// One CTA of the cluster plays one 128-thread group of node_update_step_kernel: the same per-(residue, column) FMA
+// chain (step_fma over the 32 rows of each chunk, chunk after chunk) and the same combine order ((p0+p1)+(p2+p3) over
+// the four K-slices), so both forms give bit-identical results and the choice between them (by batch size) is
+// invisible.  Inside the CTA the tile's residues are dealt to four thread groups (g = tid/128 owns g, g+4, ...).
+template <int NT>
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NC_THREADS, 1) node_update_kernel(NodeUpdArgs a) {
+    constexpr int NJ = NT / 4;
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int q = (int)cluster.block_rank();
+    extern __shared__ __align__(16) float smem[];
+    float* ring = smem;                              // [NC_RING][4096]
+    float* x = ring + NC_RING * WCHUNK_FLOATS;       // [NT][128]
+    float* hid = x + NT * HID;                       // [NT][128]  this CTA's block of the FFN hidden layer
+    float* xr = hid + NT * HID;                      // [NT][128]  this CTA's partial, read by the other three
+    float* red = xr + NT * HID;                      // [16][NJ]
+    float* cnt_s = red + 16 * NJ;                    // [NT]
+    const int g = threadIdx.x >> 7, n = threadIdx.x & 127;
+    const int node0 = (blockIdx.x >> 2) * NT;
+    const float* wb = a.weights;
+
+    const int nmine = 9 + ((a.nproj > 0 && q < a.nproj) ? 4 : 0);
+    auto chunk_src = [&](int k) -> const float* {   // step-major layout, chunk q of each step
+        if (k >= nmine) return nullptr;
+        return wb + a.w.stream + (size_t)(4 * k + q) * WCHUNK_FLOATS;
+    };
+    int issued = 0, got = 0;
+    auto issue = [&]() {
+        const float* src = chunk_src(issued);
+        if (src) {
+            float* dst = ring + (issued % NC_RING) * WCHUNK_FLOATS;
+#pragma unroll
+            for (int i = 0; i < WCHUNK_FLOATS / 4 / NC_THREADS; ++i) {
+                const int e = (threadIdx.x + i * NC_THREADS) * 4;
+                cp_async16(dst + e, src + e);
+            }
+        }
+        cp_async_commit();
+        ++issued;
+    };
+#pragma unroll
+    for (int k = 0; k < NC_RING - 1; ++k) issue();
+    auto next_chunk = [&]() -> const float* {       // block-wide; also publishes earlier shared-memory writes
+        cp_async_wait<NC_RING - 2>();
+        __syncthreads();
+        issue();
+        const float* p = ring + (got % NC_RING) * WCHUNK_FLOATS;
+        ++got;
+        return p;
+    };
+    // sum of the four CTAs' partials, in rank order (this thread: residues g + 4j, column n)
+    auto cluster_allreduce = [&](float (&v)[NJ]) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) xr[(g + 4 * j) * HID + n] = v[j];
+        cluster.sync();
+        const float* r0 = cluster.map_shared_rank(xr, 0);
+        const float* r1 = cluster.map_shared_rank(xr, 1);
+        const float* r2 = cluster.map_shared_rank(xr, 2);
+        const float* r3 = cluster.map_shared_rank(xr, 3);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int o = (g + 4 * j) * HID + n;
+            v[j] = (r0[o] + r1[o]) + (r2[o] + r3[o]);
+        }
+        cluster.sync();                              // xr may be rewritten
+    };
+
+    if (a.Spart) {
+        // neighbour sum = the three 16-row partials of the residue, added in order; weight count from E_idx
+        for (int i = threadIdx.x; i < NT * HID; i += NC_THREADS) {
+            const int node = node0 + i / HID, c = i % HID;
+            float s = 0.f;
+            if (node < a.N) {
+                const float* sp = a.Spart + (size_t)node * 3 * HID + c;
+                s = (sp[0] + sp[HID]) + sp[2 * HID];
+            }
+            x[i] = s;
+        }
+        for (int t = threadIdx.x >> 5; t < NT; t += NC_THREADS / 32) {   // one warp per residue
+            const int lane = threadIdx.x & 31, node = node0 + t;
+            float c = 0.f;
+            if (node < a.N) {
+                const float mi = a.maskf[node];
+                for (int k = lane; k < KNB; k += 32) {
+                    const int j = a.E_idx[(size_t)node * KNB + k];
+                    if (j >= 0) c += a.enc ? mi * a.maskf[j] : 1.0f;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if (lane == 0) cnt_s[t] = c;
+        }
+    } else {
+        for (int i = threadIdx.x; i < NT * HID; i += NC_THREADS) {
+            int node = node0 + i / HID;
+            x[i] = node < a.N ? a.Ssum[(size_t)node0 * HID + i] : 0.f;
+        }
+        if (threadIdx.x < NT) cnt_s[threadIdx.x] = (node0 + threadIdx.x < a.N) ? a.cnt[node0 + threadIdx.x] : 0.f;
+    }
+
+    float acc[NJ], h[NJ];
+    // ---- W3 (this CTA: input columns 32q..)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) acc[j] = 0.f;
+    step_fma<NJ>(acc, next_chunk(), x + g * HID + 32 * q, 4 * HID, n);
+    cluster_allreduce(acc);
+    {
+        const float b3 = __ldg(wb + a.w.b3 + n);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int node = node0 + g + 4 * j;
+            const float hv = node < a.N ? a.hV[(size_t)node * HID + n] : 0.f;
+            h[j] = hv + fmaf(cnt_s[g + 4 * j], b3, acc[j]) / MSG_SCALE;
+        }
+    }
+    group_layernorm<NJ>(h, wb + a.w.n1.g, wb + a.w.n1.b, red);        // ends with a barrier: x is free
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) x[(g + 4 * j) * HID + n] = h[j];
+    // ---- FFN 128 -> 512: this CTA's hidden block q
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) acc[j] = 0.f;
+    for (int s = 0; s < 4; ++s) step_fma<NJ>(acc, next_chunk(), x + g * HID + 32 * s, 4 * HID, n);
+    {
+        const float bi = __ldg(wb + a.w.bin + q * HID + n);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) hid[(g + 4 * j) * HID + n] = gelu_erf(acc[j] + bi);
+    }
+    // ---- FFN 512 -> 128: rows 128q.. = the block above
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) acc[j] = 0.f;
+    for (int s = 0; s < 4; ++s) step_fma<NJ>(acc, next_chunk(), hid + g * HID + 32 * s, 4 * HID, n);
+    cluster_allreduce(acc);
+    {
+        const float bo = __ldg(wb + a.w.bout + n);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) h[j] += acc[j] + bo;
+    }
+    group_layernorm<NJ>(h, wb + a.w.n2.g, wb + a.w.n2.b, red);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const int t = g + 4 * j, node = node0 + t;
+        const float m = node < a.N ? a.maskf[node] : 0.f;
+        h[j] *= m;
+        x[t * HID + n] = h[j];
+        if (node < a.N && q == 0) {
+            a.hV[(size_t)node * HID + n] = h[j];
+            if (a.hV_copy) a.hV_copy[(size_t)node * HID + n] = h[j];
+        }
+    }
+    // ---- projections: CTA q computes projection q
+    if (a.nproj > 0 && q < a.nproj) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc[j] = 0.f;
+        for (int s = 0; s < 4; ++s) step_fma<NJ>(acc, next_chunk(), x + g * HID + 32 * s, 4 * HID, n);
+        const ProjSpec ps = a.proj[q];
+        const float b = ps.bias >= 0 ? __ldg(wb + ps.bias + n) : 0.f;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int node = node0 + g + 4 * j;
+            if (node < a.N) {
+                float v = acc[j] + b;
+                if (ps.table >= 0) v += __ldg(wb + ps.table + (size_t)a.S[node] * HID + n);
+                ps.out[(size_t)node * HID + n] = v;
+            }
+        }
+    }
+    cp_async_wait<0>();
+    cluster.sync();      // no CTA may exit while another can still read its shared memory
+}
+
+// ---------------------------------------------------------------------------
+// node_update, single-CTA form for LARGE batches (many tiles per SM: the per-CTA fixed cost of the cluster form --
+// cluster barriers, DSMEM round trips -- would dominate): the four thread groups play the role of the four CTAs.
 // ---------------------------------------------------------------------------
 template <int NT>
-__global__ void __launch_bounds__(NK_THREADS, 1) node_update_kernel(NodeUpdArgs a) {
+__global__ void __launch_bounds__(NK_THREADS, 1) node_update_step_kernel(NodeUpdArgs a) {
     constexpr int NJ = NT / 4;
     extern __shared__ __align__(16) float smem[];
-    float* ring = smem;                              // [8][4096]
-    float* x = ring + NK_RING * WCHUNK_FLOATS;       // [NT][128]
+    float* ring = smem;                              // [2][4][4096]
+    float* x = ring + 2 * STEP_FLOATS;               // [NT][128]
     float* hid = x + NT * HID;                       // [NT][512]
     float* part = hid + NT * 4 * HID;                // [4][NT][128]
     float* red = part + 4 * NT * HID;                // [16][NJ]
-    const int kq = threadIdx.x >> 7, n = threadIdx.x & 127;
+    float* cnt_s = red + 16 * NJ;                    // [NT]
+    const int q = threadIdx.x >> 7, n = threadIdx.x & 127;
     const int node0 = blockIdx.x * NT;
     const float* wb = a.weights;
-    NodeStream ws;
-    ws.start(wb + a.w.stream, ring, a.w.nchunks);
-    float* cnt_s = red + 16 * NJ;                      // [NT]
+    StepStream ws;
+    ws.start(wb + a.w.stream, ring, a.w.nchunks / 4);
     if (a.Spart) {
-        // neighbour sum = the three 16-row partials of the residue, added in order; weight count from E_idx
         for (int i = threadIdx.x; i < NT * HID; i += NK_THREADS) {
             const int node = node0 + i / HID, c = i % HID;
             float s = 0.f;
@@ -145,7 +350,7 @@ __global__ void __launch_bounds__(NK_THREADS, 1) node_update_kernel(NodeUpdArgs 
             }
             x[i] = s;
         }
-        if (threadIdx.x < NT * 32) {                   // one warp per residue
+        if (threadIdx.x < NT * 32) {
             const int t = threadIdx.x >> 5, lane = threadIdx.x & 31, node = node0 + t;
             float c = 0.f;
             if (node < a.N) {
@@ -166,29 +371,28 @@ __global__ void __launch_bounds__(NK_THREADS, 1) node_update_kernel(NodeUpdArgs 
         }
         if (threadIdx.x < NT) cnt_s[threadIdx.x] = (node0 + threadIdx.x < a.N) ? a.cnt[node0 + threadIdx.x] : 0.f;
     }
-    int g = 0;
     float res[NJ], h[NJ];
-    node_phase<NT>(res, ws, g, 4, x, HID, part);
+    phase_ksplit<NT>(res, ws, 1, x, HID, part);                       // W3
     {
         const float b3 = __ldg(wb + a.w.b3 + n);
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
-            int node = node0 + kq + 4 * j;
-            float c = cnt_s[kq + 4 * j];
-            float hv = node < a.N ? a.hV[(size_t)node * HID + n] : 0.f;
-            h[j] = hv + fmaf(c, b3, res[j]) / MSG_SCALE;
+            const int node = node0 + q + 4 * j;
+            const float hv = node < a.N ? a.hV[(size_t)node * HID + n] : 0.f;
+            h[j] = hv + fmaf(cnt_s[q + 4 * j], b3, res[j]) / MSG_SCALE;
         }
     }
     group_layernorm<NJ>(h, wb + a.w.n1.g, wb + a.w.n1.b, red);
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) x[(kq + 4 * j) * HID + n] = h[j];
-    for (int blk = 0; blk < 4; ++blk) {
-        node_phase<NT>(res, ws, g, 4, x, HID, part);
-        const float bi = __ldg(wb + a.w.bin + blk * HID + n);
+    for (int j = 0; j < NJ; ++j) x[(q + 4 * j) * HID + n] = h[j];
+    {   // FFN 128 -> 512: group q owns hidden columns [128 q, 128 q + 128)
+        float acc[NT];
+        phase_4mat<NT>(acc, ws, x, HID);
+        const float bi = __ldg(wb + a.w.bin + q * HID + n);
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) hid[(kq + 4 * j) * 4 * HID + blk * HID + n] = gelu_erf(res[j] + bi);
+        for (int t = 0; t < NT; ++t) hid[t * 4 * HID + q * HID + n] = gelu_erf(acc[t] + bi);
     }
-    node_phase<NT>(res, ws, g, 16, hid, 4 * HID, part);
+    phase_ksplit<NT>(res, ws, 4, hid, 4 * HID, part);                  // FFN 512 -> 128
     {
         const float bo = __ldg(wb + a.w.bout + n);
 #pragma unroll
@@ -197,8 +401,8 @@ __global__ void __launch_bounds__(NK_THREADS, 1) node_update_kernel(NodeUpdArgs 
     group_layernorm<NJ>(h, wb + a.w.n2.g, wb + a.w.n2.b, red);
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-        int t = kq + 4 * j, node = node0 + t;
-        float m = node < a.N ? a.maskf[node] : 0.f;
+        const int t = q + 4 * j, node = node0 + t;
+        const float m = node < a.N ? a.maskf[node] : 0.f;
         h[j] *= m;
         x[t * HID + n] = h[j];
         if (node < a.N) {
@@ -206,17 +410,20 @@ __global__ void __launch_bounds__(NK_THREADS, 1) node_update_kernel(NodeUpdArgs 
             if (a.hV_copy) a.hV_copy[(size_t)node * HID + n] = h[j];
         }
     }
-    for (int p = 0; p < a.nproj; ++p) {
-        node_phase<NT>(res, ws, g, 4, x, HID, part);
-        const ProjSpec ps = a.proj[p];
-        const float b = ps.bias >= 0 ? __ldg(wb + ps.bias + n) : 0.f;
+    if (a.nproj > 0) {                                                 // group q computes projection q (idle if q >= nproj)
+        float acc[NT];
+        phase_4mat<NT>(acc, ws, x, HID);
+        if (q < a.nproj) {
+            const ProjSpec ps = a.proj[q];
+            const float b = ps.bias >= 0 ? __ldg(wb + ps.bias + n) : 0.f;
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            int node = node0 + kq + 4 * j;
-            if (node < a.N) {
-                float v = res[j] + b;
-                if (ps.table >= 0) v += __ldg(wb + ps.table + (size_t)a.S[node] * HID + n);
-                ps.out[(size_t)node * HID + n] = v;
+            for (int t = 0; t < NT; ++t) {
+                const int node = node0 + t;
+                if (node < a.N) {
+                    float v = acc[t] + b;
+                    if (ps.table >= 0) v += __ldg(wb + ps.table + (size_t)a.S[node] * HID + n);
+                    ps.out[(size_t)node * HID + n] = v;
+                }
             }
         }
     }
@@ -225,22 +432,22 @@ __global__ void __launch_bounds__(NK_THREADS, 1) node_update_kernel(NodeUpdArgs 
 
 // ---------------------------------------------------------------------------
 // head: x = [dec3 | dec2 | W_s[S]] -> LightAttention centre tap -> (ReLU, Linear) x3 -> affine => T[N][21]
-// (transfer_model.py:82-83, 96-116, 140-155).  Stream: LA column blocks 0..2 (12 chunks each) |
-// both_out.1 padded to 128 columns (12) | both_out.3 padded (2) | both_out.5 padded (1).
+// (transfer_model.py:82-83, 96-116, 140-155).  Steps (all K-split): LA column blocks 0..2 (3 steps each, K = 384) |
+// both_out.1 padded to 128 columns (3) | both_out.3 padded to K = 128 (1) | both_out.5 padded (1).
 // ---------------------------------------------------------------------------
 template <int NT>
 __global__ void __launch_bounds__(NK_THREADS, 1) head_kernel(HeadArgs a) {
     constexpr int NJ = NT / 4;
     extern __shared__ __align__(16) float smem[];
     float* ring = smem;
-    float* x = ring + NK_RING * WCHUNK_FLOATS;   // [NT][384]; later z1 [NT][128]
+    float* x = ring + 2 * STEP_FLOATS;           // [NT][384]; later z1 [NT][128]
     float* y = x + NT * 3 * HID;                 // [NT][384]; later z2 [NT][128]
     float* part = y + NT * 3 * HID;              // [4][NT][128]
-    const int kq = threadIdx.x >> 7, n = threadIdx.x & 127;
+    const int q = threadIdx.x >> 7, n = threadIdx.x & 127;
     const int node0 = blockIdx.x * NT;
     const float* wb = a.weights;
-    NodeStream ws;
-    ws.start(wb + a.stream, ring, 51);
+    StepStream ws;
+    ws.start(wb + a.stream, ring, 14);
     for (int i = threadIdx.x; i < NT * HID; i += NK_THREADS) {
         int t = i / HID, c = i % HID, node = node0 + t;
         bool ok = node < a.N;
@@ -248,32 +455,31 @@ __global__ void __launch_bounds__(NK_THREADS, 1) head_kernel(HeadArgs a) {
         x[t * 3 * HID + HID + c] = ok ? a.dec_prev[(size_t)node * HID + c] : 0.f;
         x[t * 3 * HID + 2 * HID + c] = ok ? __ldg(wb + a.Ws + (size_t)a.S[node] * HID + c) : 0.f;
     }
-    int g = 0;
     float res[NJ];
     for (int blk = 0; blk < 3; ++blk) {
-        node_phase<NT>(res, ws, g, 12, x, 3 * HID, part);
+        phase_ksplit<NT>(res, ws, 3, x, 3 * HID, part);
         const float b = __ldg(wb + a.la_b + blk * HID + n);
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) y[(kq + 4 * j) * 3 * HID + blk * HID + n] = fmaxf(res[j] + b, 0.f);
+        for (int j = 0; j < NJ; ++j) y[(q + 4 * j) * 3 * HID + blk * HID + n] = fmaxf(res[j] + b, 0.f);
     }
-    node_phase<NT>(res, ws, g, 12, y, 3 * HID, part);
+    phase_ksplit<NT>(res, ws, 3, y, 3 * HID, part);
     {
         const float b = n < 64 ? __ldg(wb + a.m1_b + n) : 0.f;
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) x[(kq + 4 * j) * HID + n] = fmaxf(res[j] + b, 0.f);   // z1 (columns >= 64 are 0)
+        for (int j = 0; j < NJ; ++j) x[(q + 4 * j) * HID + n] = fmaxf(res[j] + b, 0.f);   // z1 (columns >= 64 are 0)
     }
-    node_phase<NT>(res, ws, g, 2, x, HID, part);
+    phase_ksplit<NT>(res, ws, 1, x, HID, part);
     {
         const float b = n < 32 ? __ldg(wb + a.m2_b + n) : 0.f;
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) y[(kq + 4 * j) * HID + n] = fmaxf(res[j] + b, 0.f);   // z2
+        for (int j = 0; j < NJ; ++j) y[(q + 4 * j) * HID + n] = fmaxf(res[j] + b, 0.f);   // z2 (columns >= 32 are 0)
     }
-    node_phase<NT>(res, ws, g, 1, y, HID, part);
+    phase_ksplit<NT>(res, ws, 1, y, HID, part);
     if (n < 21) {
         const float b = __ldg(wb + a.m3_b + n), sc = __ldg(wb + a.ddg), sh = __ldg(wb + a.ddg + 1);
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
-            int node = node0 + kq + 4 * j;
+            int node = node0 + q + 4 * j;
             if (node < a.N) a.table[(size_t)node * 21 + n] = fmaf(res[j] + b, sc, sh);   // ddg_out: Linear(1,1)
         }
     }
@@ -281,25 +487,37 @@ __global__ void __launch_bounds__(NK_THREADS, 1) head_kernel(HeadArgs a) {
 }
 
 template <int NT> static size_t smem_node_update() {
-    return sizeof(float) * (NK_RING * WCHUNK_FLOATS + NT * HID + NT * 4 * HID + 4 * NT * HID + 16 * (NT / 4) + NT);
+    return sizeof(float) * (NC_RING * WCHUNK_FLOATS + 3 * NT * HID + 16 * (NT / 4) + NT);
+}
+template <int NT> static size_t smem_node_update_step() {
+    return sizeof(float) * (2 * STEP_FLOATS + NT * HID + NT * 4 * HID + 4 * NT * HID + 16 * (NT / 4) + NT);
 }
 template <int NT> static size_t smem_head() {
-    return sizeof(float) * (NK_RING * WCHUNK_FLOATS + 2 * NT * 3 * HID + 4 * NT * HID);
+    return sizeof(float) * (2 * STEP_FLOATS + 2 * NT * 3 * HID + 4 * NT * HID);
 }
 
 cudaError_t node_kernels_init() {
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(node_update_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_node_update<8>())) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(node_update_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_node_update<16>())) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(node_update_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_node_update<12>())) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(node_update_step_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_node_update_step<16>())) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(head_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_head<8>())) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
 void launch_node_update(const NodeUpdArgs& a, int sms, cudaStream_t st) {
-    if (a.N > 16 * sms) {
-        node_update_kernel<16><<<(a.N + 15) / 16, NK_THREADS, smem_node_update<16>(), st>>>(a);
+    // Small batches: a 4-CTA cluster per tile of NT residues, NT chosen so that the whole grid is ONE wave (152 CTAs on
+    // 148 SMs would take two).  Large batches: the single-CTA step kernel, 16 residues per block.
+    const int N = a.N;
+    if (4 * ((N + 7) / 8) <= sms) {
+        node_update_kernel<8><<<4 * ((N + 7) / 8), NC_THREADS, smem_node_update<8>(), st>>>(a);
+    } else if (4 * ((N + 11) / 12) <= sms) {
+        node_update_kernel<12><<<4 * ((N + 11) / 12), NC_THREADS, smem_node_update<12>(), st>>>(a);
+    } else if (4 * ((N + 15) / 16) <= sms) {
+        node_update_kernel<16><<<4 * ((N + 15) / 16), NC_THREADS, smem_node_update<16>(), st>>>(a);
     } else {
-        node_update_kernel<8><<<(a.N + 7) / 8, NK_THREADS, smem_node_update<8>(), st>>>(a);
+        node_update_step_kernel<16><<<(N + 15) / 16, NK_THREADS, smem_node_update_step<16>(), st>>>(a);
     }
 }
 
