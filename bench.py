@@ -151,6 +151,23 @@ def time_reference_step(w, pdb, n_sample):
     return (t1 - t0) + (t2 - t1) * (n_total / n_sample), n_total, (t1 - t0), (t2 - t1)
 
 
+def choose_threads(w, pdb):
+    """The reference leaves threading to torch's default (= all cores), which collapses on many-core hosts because its
+    ops are tiny (conv1d over a length-1 sequence, 128-wide GEMMs).  Be fair to the CPU: try a few thread counts on a
+    short sample and keep the fastest."""
+    import torch
+    ncpu = os.cpu_count() or 1
+    best, best_t = 1, None
+    for nt in [c for c in (1, 2, 4, 8, 16, 32, 64) if c <= ncpu]:
+        torch.set_num_threads(nt)
+        time_reference_step(w, pdb, 10)                       # warm
+        t = time_reference_step(w, pdb, 40)[0]
+        if best_t is None or t < best_t:
+            best, best_t = nt, t
+    torch.set_num_threads(best)
+    return best
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -158,7 +175,7 @@ def run_reference(args, rank, world):
     pdbs, desc = make_workload(args.workload, 0)
     pdbs = pdbs[:4]   # bounded: at most four proteins of the batch per step
     w = reference_weights()
-    cores = torch.get_num_threads()
+    cores = choose_threads(w, pdbs[0])
     n_sample = 300
     times, muts = [], 0
     for it in range(args.warmup + args.steps):
@@ -310,8 +327,14 @@ def run_ours(args, rank, world, local_rank):
         top = max(edge_kernels, key=lambda k: prof[k][0])
         tk = kern[top]
         tensor_core = top.startswith("tc_")
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(args.workload, {}).get(top)
         roofline = {"kernel": top, "bound": "tensor", "achieved": tk["algo_tflops"], "peak": peaks["bf16_tflops"],
-                    "unit": "TFLOP/s", "frac": tk["algo_tflops"] / peaks["bf16_tflops"], "traffic": None,
+                    "unit": "TFLOP/s", "frac": tk["algo_tflops"] / peaks["bf16_tflops"], "traffic": traffic,
+                    "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture "
+                                    "(profiles/r01_ncu_tc_edge_kernels_c3.md); null when no capture exists for this workload",
                     "peak_source": peaks["source"] + ", dense bf16 burst",
                     "note": ("tcgen05 kind::tf32 with the 3xTF32 split (fp32-accurate): 3 tensor-core MACs per algorithmic MAC at half "
                              "the bf16 rate, so frac <= 1/6 of the dense bf16 peak by construction; achieved counts the reference "
@@ -324,11 +347,12 @@ def run_ours(args, rank, world, local_rank):
         if world == 1 and not args.no_cpu:
             import torch as _t
             w = reference_weights()
+            choose_threads(w, pdbs[0])
             ts = [time_reference_step(w, pdbs[i % len(pdbs)], 300) for i in range(3)]
             est = statistics.median(t[0] for t in ts)
             cpu = {"value": ts[0][1] / est, "unit": "mutations/s", "cores": _t.get_num_threads(), "kind": "port",
                    "sample": "3 runs on one protein of the workload: full ProteinMPNN pass + 300 per-mutation head iterations, "
-                             "head time scaled to the full list; median",
+                             "head time scaled to the full list; median; thread count = fastest of {1,2,4,...,64}",
                    "mpnn_s": statistics.median(t[2] for t in ts)}
         out = {
             "metric": METRIC, "value": value, "unit": "mutations/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
