@@ -62,8 +62,11 @@ __global__ void prep_nodes_kernel(const int* __restrict__ offsets, int B, const 
 }
 
 // ---------------------------------------------------------------------------
-// knn: one warp per residue; the row of masked distances lives in shared memory,
-// the K smallest are extracted one at a time (ties -> lowest index).
+// knn: one warp per residue; the row of masked distances lives in shared memory.  The K-th smallest distance is
+// found by a bitwise (radix) search on the float pattern (all values are >= 0, so uint order == float order): 31 rounds
+// of "count keys below the trial value" with a warp-wide integer reduction.  The K winners (ties at the threshold: lowest
+// index first) are compacted with ballots and ordered by (distance, index) with a 48-element rank sort, which gives
+// exactly torch.topk's ascending output with self first.
 // ---------------------------------------------------------------------------
 __global__ void knn_kernel(const float* __restrict__ atoms, const float* __restrict__ maskf,
                            const int* __restrict__ pstart, const int* __restrict__ pend, int N, int lmax,
@@ -73,7 +76,9 @@ __global__ void knn_kernel(const float* __restrict__ atoms, const float* __restr
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = blockIdx.x * warps + w;
     if (i >= N) return;  // no block-level barriers below
-    float* d = s_row + (size_t)w * lmax;
+    float* d = s_row + (size_t)w * (lmax + 2 * KNB);
+    float* selv = d + lmax;                               // [48] selected distances
+    int* seli = reinterpret_cast<int*>(selv + KNB);       // [48] selected local indices
     const int s = pstart[i], L = pend[i] - s;
     const float xi = atoms[(size_t)i * 16 + 3], yi = atoms[(size_t)i * 16 + 4], zi = atoms[(size_t)i * 16 + 5];
     const float mi = maskf[i];
@@ -88,37 +93,56 @@ __global__ void knn_kernel(const float* __restrict__ atoms, const float* __restr
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
-    float bv = FLT_MAX;
-    int bi = 0x7fffffff;
     for (int j = lane; j < L; j += 32) {
         float m2 = mi * maskf[s + j];
-        float v = __fadd_rn(d[j], __fmul_rn(1.0f - m2, dmax));
-        d[j] = v;
-        if (v < bv) { bv = v; bi = j; }
+        d[j] = __fadd_rn(d[j], __fmul_rn(1.0f - m2, dmax));      // masked pairs pushed to the row maximum (:1105-1106)
     }
+    __syncwarp();
     const int K = L < KNB ? L : KNB;
-    for (int r = 0; r < K; ++r) {
-        float v = bv;
-        int idx = bi;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            float ov = __shfl_xor_sync(0xffffffffu, v, o);
-            int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-            if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    // ---- threshold = K-th smallest key
+    uint32_t T = 0;
+    for (int bit = 30; bit >= 0; --bit) {
+        const uint32_t trial = T | (1u << bit);
+        int cnt = 0;
+        for (int j = lane; j < L; j += 32) cnt += (__float_as_uint(d[j]) < trial) ? 1 : 0;
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (cnt < K) T = trial;
+    }
+    int n_less = 0;
+    for (int j = lane; j < L; j += 32) n_less += (__float_as_uint(d[j]) < T) ? 1 : 0;
+    n_less = __reduce_add_sync(0xffffffffu, n_less);
+    const int need_eq = K - n_less;                       // how many keys equal to T to take, in index order
+    // ---- compaction
+    int out_pos = 0, eq_seen = 0;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    for (int base = 0; base < L; base += 32) {
+        const int j = base + lane;
+        const uint32_t key = j < L ? __float_as_uint(d[j]) : 0xffffffffu;
+        const bool is_lt = key < T, is_eq = key == T;
+        const uint32_t b_eq = __ballot_sync(0xffffffffu, is_eq);
+        const bool take = is_lt || (is_eq && (eq_seen + __popc(b_eq & lt_mask)) < need_eq);
+        const uint32_t b_take = __ballot_sync(0xffffffffu, take);
+        if (take) {
+            const int pos = out_pos + __popc(b_take & lt_mask);
+            selv[pos] = __uint_as_float(key);
+            seli[pos] = j;
         }
-        if (lane == 0) {
-            E_idx[(size_t)i * KNB + r] = s + idx;
-            D_nb[(size_t)i * KNB + r] = v;
+        out_pos += __popc(b_take);
+        eq_seen += __popc(b_eq);
+    }
+    __syncwarp();
+    // ---- order by (distance, index): rank sort of K <= 48 entries
+    for (int e = lane; e < K; e += 32) {
+        const float v = selv[e];
+        const int idx = seli[e];
+        int rank = 0;
+        for (int o = 0; o < K; ++o) {
+            const float ov = selv[o];
+            const int oi = seli[o];
+            rank += (ov < v || (ov == v && oi < idx)) ? 1 : 0;
         }
-        if ((idx & 31) == lane) {  // owner removes it and rescans its own stripe
-            d[idx] = FLT_MAX;
-            bv = FLT_MAX;
-            bi = 0x7fffffff;
-            for (int j = lane; j < L; j += 32) {
-                float t = d[j];
-                if (t < bv) { bv = t; bi = j; }
-            }
-        }
+        E_idx[(size_t)i * KNB + rank] = s + idx;
+        D_nb[(size_t)i * KNB + rank] = v;
     }
     for (int r = K + lane; r < KNB; r += 32) {
         E_idx[(size_t)i * KNB + r] = -1;
@@ -458,13 +482,14 @@ void launch_prep_nodes(const int* offsets, int B, const float* X, const uint8_t*
     prep_nodes_kernel<<<(N + 127) / 128, 128, 0, st>>>(offsets, B, X, mask, N, pstart, pend, atoms, maskf);
 }
 
-int knn_max_len() { return 200 * 1024 / 4; }
+int knn_max_len() { return 200 * 1024 / 4 - 2 * KNB; }
 
 void launch_knn(const float* atoms, const float* maskf, const int* pstart, const int* pend, int N, int lmax,
                 int* E_idx, float* D_nb, cudaStream_t st) {
     int warps = 8;
-    while (warps > 1 && (size_t)warps * lmax * 4 > 200 * 1024) warps >>= 1;
-    size_t smem = (size_t)warps * lmax * 4;
+    const size_t per_warp = (size_t)(lmax + 2 * KNB) * 4;
+    while (warps > 1 && (size_t)warps * per_warp > 200 * 1024) warps >>= 1;
+    size_t smem = (size_t)warps * per_warp;
     knn_kernel<<<(N + warps - 1) / warps, warps * 32, smem, st>>>(atoms, maskf, pstart, pend, N, lmax, E_idx, D_nb);
 }
 

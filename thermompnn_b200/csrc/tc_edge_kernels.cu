@@ -569,7 +569,7 @@ __constant__ int8_t c_tc_pair_b[NPAIR] = {1, 0, 2, 3, 4, 0, 2, 3, 4, 2, 3, 4, 2,
 
 struct __align__(1024) TcFeatSmem {
     uint8_t wring[TC_WSLOTS][TC_WCHUNK_BYTES];   // 96 KB
-    float out[4][TC_ROWS * 32];                  // 64 KB output staging (same swizzled slabs as TcSmem::hE)
+    float out[TC_ROWS * 64];                     // 32 KB output staging: [128 rows][64 cols], 16-byte chunks XOR (row & 15)
     float ajT[16][TC_ROWS];                      // neighbour atoms, component-major: [3*atom + xyz][row]
     float ai[4][16];                             // atoms of the (up to 4) residues the tile touches
     float dnb[TC_ROWS];
@@ -577,6 +577,7 @@ struct __align__(1024) TcFeatSmem {
     float pos_table[66 * 16];
     float vec[3][HID];                           // LN gain, LN shift, W_e bias
     float mu[16];
+    float2 lnx[2][TC_ROWS];
     uint64_t w_full[TC_WSLOTS], w_empty[TC_WSLOTS];
     uint64_t a_ready[4], a_free[4];
     uint64_t d_ready[2];
@@ -600,7 +601,9 @@ struct TcFeatArgs {
     int N, num_tiles;
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_feat_kernel(TcFeatArgs a) {
+// Warp roles as in tc_edge_kernel: warps 0-7 epilogue (set s = warp/4 handles the 32-column chunks c with c%2 == s),
+// warp 8 MMA issuer, warp 9 weight producer, warp 10 per-row input producer.
+__global__ void __launch_bounds__(T2_THREADS, 1) tc_edge_feat_kernel(TcFeatArgs a) {
     constexpr int K1_CHUNKS = EDGE_IN / 32;   // 13
     extern __shared__ uint8_t smem_raw[];
     TcFeatSmem& S = *reinterpret_cast<TcFeatSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -613,19 +616,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_feat_kernel(TcFeatArgs 
         for (int i = 0; i < 4; ++i) { mbar_init(&S.a_ready[i], 128); mbar_init(&S.a_free[i], 1); }
         for (int i = 0; i < 2; ++i) mbar_init(&S.d_ready[i], 1);
         mbar_init(&S.in_full, 32);
-        mbar_init(&S.in_empty, 128);
+        mbar_init(&S.in_empty, 256);
         fence_barrier_init();
     }
-    for (int i = threadIdx.x; i < HID; i += TC_THREADS) { S.vec[0][i] = a.ln_g[i]; S.vec[1][i] = a.ln_b[i]; S.vec[2][i] = a.b_e[i]; }
-    for (int i = threadIdx.x; i < 66 * 16; i += TC_THREADS) S.pos_table[i] = a.pos_table[i];
+    for (int i = threadIdx.x; i < HID; i += T2_THREADS) { S.vec[0][i] = a.ln_g[i]; S.vec[1][i] = a.ln_b[i]; S.vec[2][i] = a.b_e[i]; }
+    for (int i = threadIdx.x; i < 66 * 16; i += T2_THREADS) S.pos_table[i] = a.pos_table[i];
     if (threadIdx.x < 16) S.mu[threadIdx.x] = a.rbf_mu[threadIdx.x];
-    if (warp == 4) tmem_alloc<512>(&S.tmem_base);
+    if (warp == 8) tmem_alloc<512>(&S.tmem_base);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = S.tmem_base;
 
-    if (warp == 5) {
+    if (warp == 9) {
         if (lane == 0) {                                  // weight producer
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
@@ -636,7 +639,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_feat_kernel(TcFeatArgs 
                     bulk_g2s(S.wring[slot], a.wimg + (size_t)c * TC_WCHUNK_BYTES, TC_WCHUNK_BYTES, &S.w_full[slot]);
                 }
         }
-    } else if (warp == 4) {
+    } else if (warp == 8) {
         {                                                 // MMA issuer (whole warp runs the loop; lane 0 issues)
             // GEMM1 (416 deep): hi.hi products accumulate in D0, the small corrections (lo.hi, hi.lo) in D1 -- with 13
             // K-chunks the truncating accumulator would otherwise lose them against the large partial sums (this GEMM was
@@ -680,7 +683,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_feat_kernel(TcFeatArgs 
                     if (leader) mma_commit(&S.d_ready[l]);
                 }
         }
-    } else if (warp == 6) {
+    } else if (warp == 10) {
         uint32_t ti = 0;                                  // per-row inputs
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
             const int row0 = tile * TC_ROWS;
@@ -713,8 +716,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_feat_kernel(TcFeatArgs 
             mbar_arrive(&S.in_full);
         }
     } else {
-        const int r = threadIdx.x;
-        const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+        const int set = warp >> 2, quad = warp & 3;
+        const int r = quad * 32 + lane;
+        const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
         uint32_t ti = 0, pub = 0;      // pub: bit s = parity of a_free[s]'s next completion, bit 8+s = slot s used before
         auto publish = [&](int slot, const float (&v)[32]) {
             if ((pub >> (8 + slot)) & 1) {                       // wait until the MMAs that read this slot are done
@@ -731,8 +735,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_feat_kernel(TcFeatArgs 
             int node_l = row / KNB - row0 / KNB;
             node_l = node_l > 3 ? 3 : node_l;
             mbar_wait(&S.in_full, ti & 1);
-            // ---- features -> A, 32 columns at a time
-            for (int c = 0; c < K1_CHUNKS; ++c) {
+            // ---- features -> A, 32 columns at a time; this set takes the chunks of its parity
+            for (int c = set; c < K1_CHUNKS; c += 2) {
                 float v[32];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -763,17 +767,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_feat_kernel(TcFeatArgs 
                 publish(c & 3, v);
             }
             mbar_arrive(&S.in_empty);
-            // ---- norm_edges (thread-local LayerNorm over the 128 accumulator columns) -> A of the W_e GEMM
+            // ---- norm_edges: LayerNorm over the 128 accumulator columns (two threads per row) -> A of the W_e GEMM
             mbar_wait(&S.d_ready[0], ti & 1);
             tc_fence_after();
             {
                 float shift = 0.f, s1 = 0.f, s2 = 0.f;
-                for (int c = 0; c < 4; ++c) {
+                for (int c = set; c < 4; c += 2) {
                     uint32_t acc[32], cor[32];
                     tmem_ld32(lane_addr + COL_D0 + c * 32, acc);
                     tmem_ld32(lane_addr + COL_D1 + c * 32, cor);
                     tmem_wait_ld();
-                    if (c == 0) shift = __uint_as_float(acc[0]) + __uint_as_float(cor[0]);
+                    if (c == set) shift = __uint_as_float(acc[0]) + __uint_as_float(cor[0]);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const float x = __uint_as_float(acc[j]) + __uint_as_float(cor[j]);
@@ -785,14 +789,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_feat_kernel(TcFeatArgs 
                     tmem_st32(lane_addr + COL_D0 + c * 32, acc);
                 }
                 tmem_wait_st();
+                const float mean_a = shift + s1 * (1.0f / 64.0f);
+                const float m2_a = fmaxf(s2 - s1 * s1 * (1.0f / 64.0f), 0.f);
+                S.lnx[set][r] = make_float2(mean_a, m2_a);
                 tc_fence_before();
-                epi_bar_sync();          // every row has finished reading D1: the W_e GEMM may overwrite it
+                named_bar(3, 256);       // partner's statistics visible; every row has finished reading D1 (the W_e GEMM overwrites it)
                 tc_fence_after();
-                const float ms = s1 * (1.0f / HID);
-                const float mean = shift + ms;
-                const float var = fmaxf(s2 * (1.0f / HID) - ms * ms, 0.f);
+                const float2 ob = S.lnx[set ^ 1][r];
+                const float dm = mean_a - ob.x;
+                const float mean = 0.5f * (mean_a + ob.x);
+                const float var = (m2_a + ob.y + 32.0f * dm * dm) * (1.0f / HID);
                 const float rstd = 1.0f / sqrtf(var + LN_EPS);
-                for (int c = 0; c < 4; ++c) {
+                for (int c = set; c < 4; c += 2) {
                     uint32_t acc[32];
                     tmem_ld32(lane_addr + COL_D0 + c * 32, acc);
                     tmem_wait_ld();
@@ -803,36 +811,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_edge_feat_kernel(TcFeatArgs 
                     publish(c, v);
                 }
             }
-            // ---- W_e output + bias -> staging -> coalesced store
+            // ---- W_e output + bias -> staging (two 64-column halves) -> coalesced store
             mbar_wait(&S.d_ready[1], ti & 1);
             tc_fence_after();
-            {
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t acc[32];
-                    tmem_ld32(lane_addr + COL_D1 + c * 32, acc);
-                    tmem_wait_ld();
-                    float o[32];
+            for (int hf = 0; hf < 2; ++hf) {
+                const int c = 2 * hf + set;                     // this thread's 32-column chunk of the half
+                uint32_t acc[32];
+                tmem_ld32(lane_addr + COL_D1 + c * 32, acc);
+                tmem_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(acc[j]) + S.vec[2][c * 32 + j];
-                    store_row_chunk(S.out[c], r, o);
+                for (int j = 0; j < 8; ++j) {
+                    const int ch = set * 8 + j;                 // 16-byte chunk 0..15 inside the 64-column half
+                    *reinterpret_cast<float4*>(S.out + r * 64 + ((ch ^ (r & 15)) << 2)) =
+                        make_float4(__uint_as_float(acc[4 * j]) + S.vec[2][c * 32 + 4 * j], __uint_as_float(acc[4 * j + 1]) + S.vec[2][c * 32 + 4 * j + 1],
+                                    __uint_as_float(acc[4 * j + 2]) + S.vec[2][c * 32 + 4 * j + 2], __uint_as_float(acc[4 * j + 3]) + S.vec[2][c * 32 + 4 * j + 3]);
                 }
+                named_bar(3, 256);
+                {
+                    const int t = set * 128 + r;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int idx = i * 256 + t, rr = idx >> 4, ch = idx & 15;
+                        if (row0 + rr < total_rows)
+                            *reinterpret_cast<float4*>(a.hE + (size_t)(row0 + rr) * HID + hf * 64 + ch * 4) =
+                                *reinterpret_cast<const float4*>(S.out + rr * 64 + ((ch ^ (rr & 15)) << 2));
+                    }
+                }
+                named_bar(3, 256);
             }
             tc_fence_before();
-            epi_bar_sync();
-            for (int i = 0; i < 32; ++i) {
-                const int idx = i * 128 + r, rr = idx >> 5, ch = idx & 31;
-                if (row0 + rr < total_rows) {
-                    float4 t = *reinterpret_cast<const float4*>(&S.out[ch >> 3][slab_off(rr, ch & 7)]);
-                    *reinterpret_cast<float4*>(a.hE + (size_t)(row0 + rr) * HID + ch * 4) = t;
-                }
-            }
-            epi_bar_sync();   // staging is rewritten by the next tile
         }
     }
     __syncwarp();
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc<512>(tmem);
+    if (warp == 8) tmem_dealloc<512>(tmem);
 }
 
 cudaError_t tc_kernels_init() {
@@ -852,7 +865,7 @@ void launch_tc_edge_feat(const float* atoms, const int* E_idx, const float* D_nb
     a.wimg = reinterpret_cast<const uint8_t*>(wimg); a.ln_g = ln_g; a.ln_b = ln_b; a.b_e = b_e; a.hE = hE; a.N = N;
     a.num_tiles = (N * KNB + TC_ROWS - 1) / TC_ROWS;
     const int grid = a.num_tiles < sms ? a.num_tiles : sms;
-    tc_edge_feat_kernel<<<grid, TC_THREADS, sizeof(TcFeatSmem) + 1024, st>>>(a);
+    tc_edge_feat_kernel<<<grid, T2_THREADS, sizeof(TcFeatSmem) + 1024, st>>>(a);
 }
 
 static TcArgs tc_args(float* hE, const int* E_idx, const float* P, int p_stride, const float* Q, int q_stride, const float* maskf,
