@@ -130,7 +130,7 @@ struct __align__(1024) Tc2Smem {
     float wrow[2][TC_ROWS];
     float mrow[2][TC_ROWS];
     float vec[4][HID];
-    float2 lnx[2][TC_ROWS];              // LayerNorm partial (mean, M2) exchange between the two sets
+    float2 lnx[4][TC_ROWS];              // LayerNorm partial (mean, M2) exchange between the epilogue sets
     int jidx[TC_ROWS];
     uint64_t w_full[T2_NW], w_empty[T2_NW];
     uint64_t act_full[T2_NACT], act_empty[T2_NACT];
@@ -180,9 +180,13 @@ __device__ __forceinline__ void named_bar(int id, int threads) { asm volatile("b
 __device__ __forceinline__ void publish_A16(uint32_t lane_addr, int sc, const float (&v)[16], uint64_t* a_ready) {
     uint32_t hi[16], lo[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
+    for (int j = 0; j < 16; j += 2) {
         hi[j] = __float_as_uint(v[j]) & 0xffffe000u;
-        lo[j] = __float_as_uint(v[j] - __uint_as_float(hi[j]));
+        hi[j + 1] = __float_as_uint(v[j + 1]) & 0xffffe000u;
+        float l0, l1;                                   // lo = v - hi, exact (packed: fma(hi, -1, v))
+        upk2(fma2(pk2(__uint_as_float(hi[j]), __uint_as_float(hi[j + 1])), pk2(-1.0f, -1.0f), pk2(v[j], v[j + 1])), l0, l1);
+        lo[j] = __float_as_uint(l0);
+        lo[j + 1] = __float_as_uint(l1);
     }
     tmem_st16(lane_addr + COL_AHI + sc * 16, hi);
     tmem_st16(lane_addr + COL_ALO + sc * 16, lo);
@@ -206,9 +210,13 @@ __device__ __forceinline__ void load_vec16(float (&v)[16], const float* p) {
     }
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(T2_THREADS, 1) tc_edge_kernel(TcArgs a) {
+// NSETS epilogue sets of four warps: set s handles the 16-column sub-chunks sc with sc % NSETS == s.
+template <int KIND, int NSETS>
+__global__ void __launch_bounds__((4 * NSETS + 3) * 32, 1) tc_edge_kernel(TcArgs a) {
     constexpr int STAGES = (KIND == TC_UPD) ? 3 : 2;
+    constexpr int W_MMA = 4 * NSETS, W_WPROD = 4 * NSETS + 1, W_APROD = 4 * NSETS + 2;
+    constexpr int NTHREADS = (4 * NSETS + 3) * 32, EPI_THREADS = 128 * NSETS;
+    constexpr int SPT = 8 / NSETS;                       // sub-chunks per thread and stage
     extern __shared__ uint8_t smem_raw[];
     Tc2Smem& S = *reinterpret_cast<Tc2Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -222,17 +230,17 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tc_edge_kernel(TcArgs a) {
         for (int i = 0; i < 2; ++i) mbar_init(&S.d_ready[i], 1);
         fence_barrier_init();
     }
-    for (int i = threadIdx.x; i < HID; i += T2_THREADS) {
+    for (int i = threadIdx.x; i < HID; i += NTHREADS) {
         S.vec[0][i] = a.v0[i];
         if (KIND == TC_UPD) { S.vec[1][i] = a.v1[i]; S.vec[2][i] = a.v2[i]; S.vec[3][i] = a.v3[i]; }
     }
-    if (warp == 8) tmem_alloc<512>(&S.tmem_base);
+    if (warp == W_MMA) tmem_alloc<512>(&S.tmem_base);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = S.tmem_base;
 
-    if (warp == 9) {
+    if (warp == W_WPROD) {
         // ---------------- weight producer ----------------
         if (lane == 0) {
             uint32_t it = 0;
@@ -244,7 +252,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tc_edge_kernel(TcArgs a) {
                     bulk_g2s(S.w[s], a.wimg + (size_t)c * 2 * T2_HALF, 2 * T2_HALF, &S.w_full[s]);
                 }
         }
-    } else if (warp == 8) {
+    } else if (warp == W_MMA) {
         // ---------------- MMA issuer: one 16-column sub-chunk (2 K-steps) at a time, as the epilogue publishes them ----
         // The whole warp runs the loop so that every operand is warp-uniform (lives in uniform registers); only the
         // tcgen05 instructions themselves are predicated on lane 0.  Computing operands inside an `if (lane == 0)` region
@@ -290,7 +298,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tc_edge_kernel(TcArgs a) {
                     TC_STAMP(g / STAGES, 25 + 2 * l);
                 }
         }
-    } else if (warp == 10) {
+    } else if (warp == W_APROD) {
         // ---------------- activation producer ----------------
         // Every lane owns rows lane, lane+32, lane+64, lane+96 of a tile and copies their 128-byte chunk slices with
         // eight 16-byte cp.async each (h_E rows, or the neighbour's Q row): no index math inside the copy loop.
@@ -375,13 +383,15 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tc_edge_kernel(TcArgs a) {
         auto act_release = [&](uint32_t k) { mbar_arrive(&S.act_empty[k % T2_NACT]); };
         // input stage of a tile: its four h_E chunks -> A (each thread converts its 16-column half of every chunk)
         auto input_stage = [&]() {
-            for (int c = 0; c < 4; ++c, ++kc) {
-                const float* chunk = act_wait(kc);
+            for (int c = 0; c < SPT; ++c) {
+                const int sc = set + NSETS * c;
+                const float* chunk = act_wait(kc + (sc >> 1));
                 float v[16];
-                load_act16(v, chunk, r, set);
-                act_release(kc);
-                publish_A16(lane_addr, 2 * c + set, v, &S.a_ready[2 * c + set]);
+                load_act16(v, chunk, r, sc & 1);
+                act_release(kc + (sc >> 1));
+                publish_A16(lane_addr, sc, v, &S.a_ready[sc]);
             }
+            kc += 4;
         };
         int tile = blockIdx.x;
         const int sb0 = (quad == 0) ? (set ? 16 : 0) : 64;   // only warps 0 and 4 stamp
@@ -401,24 +411,26 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tc_edge_kernel(TcArgs a) {
             EPI_STAMP(2);
             {
                 const uint32_t dcol = (g & 1) ? COL_D1 : COL_D0;
-                for (int c = 0; c < 4; ++c, ++kc) {
-                    const int sc = 2 * c + set;
+                for (int c = 0; c < SPT; ++c) {
+                    const int sc = set + NSETS * c;
                     uint32_t acc[16];
                     tmem_ld16(lane_addr + dcol + sc * 16, acc);
-                    const float* chunk = act_wait(kc);
+                    const float* chunk = act_wait(kc + (sc >> 1));
                     float qv[16], pv[16], v[16];
-                    load_act16(qv, chunk, r, set);
-                    act_release(kc);
+                    load_act16(qv, chunk, r, sc & 1);
+                    act_release(kc + (sc >> 1));
                     load_vec16(pv, &S.p[mb][node_l][sc * 16]);
                     tmem_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float pre = (KIND == TC_DEC) ? fmaf(m_i, __uint_as_float(acc[j]) + qv[j], pv[j])
-                                                           : (__uint_as_float(acc[j]) + pv[j] + qv[j]);
-                        v[j] = gelu_fast(pre);
+                    for (int j = 0; j < 16; j += 2) {      // packed pairs: same per-lane operation order as the scalar form
+                        const f32x2 a2 = pk2(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]));
+                        const f32x2 q2 = pk2(qv[j], qv[j + 1]), p2 = pk2(pv[j], pv[j + 1]);
+                        const f32x2 pre = (KIND == TC_DEC) ? fma2(pk2(m_i, m_i), add2(a2, q2), p2) : add2(add2(a2, p2), q2);
+                        upk2(gelu_fast2(pre), v[j], v[j + 1]);
                     }
                     publish_A16(lane_addr, sc, v, &S.a_ready[sc]);
                 }
+                kc += 4;
             }
             ++g;
             EPI_STAMP(3);
@@ -429,15 +441,16 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tc_edge_kernel(TcArgs a) {
                 EPI_STAMP(4);
                 {
                     const uint32_t dcol = (g & 1) ? COL_D1 : COL_D0;
-                    for (int c = 0; c < 4; ++c) {
-                        const int sc = 2 * c + set;
+                    for (int c = 0; c < SPT; ++c) {
+                        const int sc = set + NSETS * c;
                         uint32_t acc[16];
                         tmem_ld16(lane_addr + dcol + sc * 16, acc);
                         float bv[16], v[16];
                         load_vec16(bv, &S.vec[0][sc * 16]);
                         tmem_wait_ld();
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = gelu_fast(__uint_as_float(acc[j]) + bv[j]);
+                        for (int j = 0; j < 16; j += 2)
+                            upk2(gelu_fast2(add2(pk2(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1])), pk2(bv[j], bv[j + 1]))), v[j], v[j + 1]);
                         publish_A16(lane_addr, sc, v, &S.a_ready[sc]);
                     }
                 }
@@ -455,14 +468,14 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tc_edge_kernel(TcArgs a) {
             if (KIND == TC_UPD) {
                 // ---- final: + b13 + residual, LayerNorm over the row (two threads per row), direct 64-byte row stores
                 float shift = 0.f, s1 = 0.f, s2 = 0.f;
-                for (int c = 0; c < 4; ++c, ++kc) {
-                    const int sc = 2 * c + set;
+                for (int c = 0; c < SPT; ++c) {
+                    const int sc = set + NSETS * c;
                     uint32_t acc[16];
                     tmem_ld16(lane_addr + dcol + sc * 16, acc);
-                    const float* chunk = act_wait(kc);
+                    const float* chunk = act_wait(kc + (sc >> 1));
                     float old[16], bv[16];
-                    load_act16(old, chunk, r, set);
-                    act_release(kc);
+                    load_act16(old, chunk, r, sc & 1);
+                    act_release(kc + (sc >> 1));
                     load_vec16(bv, &S.vec[1][sc * 16]);
                     tmem_wait_ld();
                     if (c == 0) shift = __uint_as_float(acc[0]) + bv[0] + old[0];
@@ -476,22 +489,27 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tc_edge_kernel(TcArgs a) {
                     }
                     tmem_st16(lane_addr + dcol + sc * 16, acc);
                 }
+                kc += 4;
                 tmem_wait_st();
-                // this thread's 64 values: mean_a, M2_a; combine with the partner's (Chan et al.)
-                const float mean_a = shift + s1 * (1.0f / 64.0f);
-                const float m2_a = fmaxf(s2 - s1 * s1 * (1.0f / 64.0f), 0.f);
+                // this thread's 128/NSETS values: (mean, M2); combine the NSETS partials of the row in set order (Chan et al.)
+                constexpr float MV = (float)(HID / NSETS);
+                const float mean_a = shift + s1 * (1.0f / MV);
+                const float m2_a = fmaxf(s2 - s1 * s1 * (1.0f / MV), 0.f);
                 S.lnx[set][r] = make_float2(mean_a, m2_a);
-                named_bar(3, 256);
-                const float2 ob = S.lnx[set ^ 1][r];
-                const float dm = mean_a - ob.x;
-                const float mean = 0.5f * (mean_a + ob.x);
-                const float var = (m2_a + ob.y + 32.0f * dm * dm) * (1.0f / HID);
+                named_bar(3, EPI_THREADS);
+                float mean = 0.f, m2 = 0.f;
+#pragma unroll
+                for (int q = 0; q < NSETS; ++q) mean += S.lnx[q][r].x;
+                mean *= (1.0f / NSETS);
+#pragma unroll
+                for (int q = 0; q < NSETS; ++q) { const float2 o = S.lnx[q][r]; const float dm = o.x - mean; m2 += o.y + MV * dm * dm; }
+                const float var = m2 * (1.0f / HID);
                 const float rstd = 1.0f / sqrtf(var + LN_EPS);
                 float* ost = &S.out[0][0];                      // [128 rows][64 cols], 16-byte chunks XOR-swizzled by row
                 for (int hf = 0; hf < 2; ++hf) {
 #pragma unroll
-                    for (int cc = 0; cc < 2; ++cc) {
-                        const int sc = 4 * hf + 2 * cc + set;       // this thread's two sub-chunks of the half
+                    for (int cc = 0; cc < SPT / 2; ++cc) {
+                        const int sc = 4 * hf + NSETS * cc + set;   // this thread's sub-chunk(s) of the half
                         uint32_t xv[16];
                         tmem_ld16(lane_addr + dcol + sc * 16, xv);
                         float gv[16], bv[16];
@@ -508,43 +526,45 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tc_edge_kernel(TcArgs a) {
                                             (__uint_as_float(xv[4 * j + 3]) - mean) * rstd * gv[4 * j + 3] + bv[4 * j + 3]);
                         }
                     }
-                    named_bar(3, 256);
-                    {   // 128 rows x 256 B: 16 lanes per row, 8 passes
+                    named_bar(3, EPI_THREADS);
+                    {   // 128 rows x 256 B: 16 lanes per row
                         const int t = set * 128 + r;
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int idx = i * 256 + t, rr = idx >> 4, ch = idx & 15;
+                        for (int i = 0; i < 2048 / EPI_THREADS; ++i) {
+                            const int idx = i * EPI_THREADS + t, rr = idx >> 4, ch = idx & 15;
                             if (row0 + rr < total_rows)
                                 *reinterpret_cast<float4*>(a.hE + (size_t)(row0 + rr) * HID + hf * 64 + ch * 4) =
                                     *reinterpret_cast<const float4*>(ost + rr * 64 + ((ch ^ (rr & 15)) << 2));
                         }
                     }
-                    named_bar(3, 256);
+                    named_bar(3, EPI_THREADS);
                 }
             } else {
                 // ---- final: + b2, GELU, weight, per-residue column sums of each 16-row half-warp
                 const int sb = (row0 + quad * 32) / 16 + (lane >> 4);   // 16-row sub-block of the edge array
                 const int node = sb / 3, part = sb - node * 3;
-                for (int c = 0; c < 4; c += 2) {                       // two 16-column sub-chunks per transpose-reduce
+                for (int c = 0; c < SPT; c += 2) {                     // two 16-column sub-chunks per transpose-reduce
                     float gv[32];
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const int sc = 2 * (c + h) + set;
+                        const int sc = NSETS * (c + h) + set;
                         uint32_t acc[16];
                         tmem_ld16(lane_addr + dcol + sc * 16, acc);
                         float bv[16];
                         load_vec16(bv, &S.vec[0][sc * 16]);
                         tmem_wait_ld();
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float gl = gelu_fast(__uint_as_float(acc[j]) + bv[j]);
-                            gv[h * 16 + j] = (w_r != 0.f) ? w_r * gl : 0.f;
+                        for (int j = 0; j < 16; j += 2) {
+                            float g0, g1;
+                            upk2(gelu_fast2(add2(pk2(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1])), pk2(bv[j], bv[j + 1]))), g0, g1);
+                            gv[h * 16 + j] = (w_r != 0.f) ? w_r * g0 : 0.f;
+                            gv[h * 16 + j + 1] = (w_r != 0.f) ? w_r * g1 : 0.f;
                         }
                     }
                     halfwarp_colsum32(gv, lane);       // lane l: local columns 2(l&15), 2(l&15)+1 of the 32 gathered above
                     if (node < N) {
                         const int lc = 2 * (lane & 15), h = lc >> 4;             // which of the two sub-chunks, column inside it
-                        const int col = (2 * (c + h) + set) * 16 + (lc & 15);
+                        const int col = (NSETS * (c + h) + set) * 16 + (lc & 15);
                         *reinterpret_cast<float2*>(a.Spart + ((size_t)node * 3 + part) * HID + col) = make_float2(gv[0], gv[1]);
                     }
                 }
@@ -556,7 +576,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tc_edge_kernel(TcArgs a) {
     __syncwarp();
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc<512>(tmem);
+    if (warp == W_MMA) tmem_dealloc<512>(tmem);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -848,12 +868,14 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tc_edge_feat_kernel(TcFeatArgs 
     if (warp == 8) tmem_dealloc<512>(tmem);
 }
 
+constexpr int UPD_SETS = 4, MSG_SETS = 4;   // epilogue sets (4 warps each) per kernel kind
+
 cudaError_t tc_kernels_init() {
     cudaError_t e;
     const int bytes = (int)sizeof(Tc2Smem) + 1024;
-    if ((e = cudaFuncSetAttribute(tc_edge_kernel<TC_UPD>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(tc_edge_kernel<TC_ENC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(tc_edge_kernel<TC_DEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(tc_edge_kernel<TC_UPD, UPD_SETS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(tc_edge_kernel<TC_ENC, MSG_SETS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(tc_edge_kernel<TC_DEC, MSG_SETS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
     return cudaFuncSetAttribute(tc_edge_feat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcFeatSmem) + 1024);
 }
 
@@ -884,7 +906,7 @@ void launch_tc_edge_upd(float* hE, const int* E_idx, const float* P, const float
     TcArgs a = tc_args(hE, E_idx, P, HID, Q, HID, maskf, wimg, N);
     a.v0 = b12; a.v1 = b13; a.v2 = ln_g; a.v3 = ln_b; a.trace = trace;
     const int grid = a.num_tiles < sms ? a.num_tiles : sms;
-    tc_edge_kernel<TC_UPD><<<grid, T2_THREADS, sizeof(Tc2Smem) + 1024, st>>>(a);
+    tc_edge_kernel<TC_UPD, UPD_SETS><<<grid, (4 * UPD_SETS + 3) * 32, sizeof(Tc2Smem) + 1024, st>>>(a);
 }
 
 void launch_tc_msg(bool dec, const float* hE, const int* E_idx, const float* P, int p_stride, const float* Q, int q_stride,
@@ -893,8 +915,8 @@ void launch_tc_msg(bool dec, const float* hE, const int* E_idx, const float* P, 
     TcArgs a = tc_args(const_cast<float*>(hE), E_idx, P, p_stride, Q, q_stride, maskf, wimg, N);
     a.v0 = b2; a.Spart = Spart; a.trace = trace;
     const int grid = a.num_tiles < sms ? a.num_tiles : sms;
-    if (dec) tc_edge_kernel<TC_DEC><<<grid, T2_THREADS, sizeof(Tc2Smem) + 1024, st>>>(a);
-    else tc_edge_kernel<TC_ENC><<<grid, T2_THREADS, sizeof(Tc2Smem) + 1024, st>>>(a);
+    if (dec) tc_edge_kernel<TC_DEC, MSG_SETS><<<grid, (4 * MSG_SETS + 3) * 32, sizeof(Tc2Smem) + 1024, st>>>(a);
+    else tc_edge_kernel<TC_ENC, MSG_SETS><<<grid, (4 * MSG_SETS + 3) * 32, sizeof(Tc2Smem) + 1024, st>>>(a);
 }
 
 }  // namespace tmpnn
