@@ -722,6 +722,7 @@ int tmpnn_run_batch(tmpnn_ctx* ctx, int32_t B, const int32_t* offsets, const flo
         if (!out_dev) CU(cudaMemcpyAsync(out_table, d_table, n * 21 * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
     CU(cudaGetLastError());
+    CU(tc_take_error());
     if (!(flags & TMPNN_NO_SYNC) || !out_dev) {
         CU(cudaStreamSynchronize(st));
         ctx->stage_busy = false;

@@ -43,6 +43,7 @@ struct HeadArgs {
 cudaError_t kernels_init();
 cudaError_t node_kernels_init();
 cudaError_t tc_kernels_init();
+cudaError_t tc_take_error();   // sticky host-side error of the tensor-core launchers (tensor-map encoding), cleared on read
 int knn_max_len();
 
 void launch_prep_nodes(const int* offsets, int B, const float* X, const uint8_t* mask, int N, int* pstart, int* pend,

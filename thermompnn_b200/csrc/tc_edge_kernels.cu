@@ -139,6 +139,7 @@ struct __align__(1024) Tc2Smem {
 };
 
 struct TcArgs {
+    alignas(64) CUtensorMap tm_hE;   // h_E as a [N*48][128] fp32 tensor, box [128 rows][32 cols], 128-byte swizzle
     float* hE;              // [N*48][128]; UPD updates it in place
     const int* E_idx;       // [N*48]
     const float* P; int p_stride;   // per-residue projection of h_V[i] (+bias); stride 0 = one shared row
@@ -202,6 +203,14 @@ __device__ __forceinline__ void load_act16(float (&v)[16], const float* chunk, i
         v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
     }
 }
+// the same for a chunk written by TMA: dense 128-byte rows, 16-byte units XOR (row & 7)
+__device__ __forceinline__ void load_act16_sw(float (&v)[16], const float* chunk, int r, int half) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float4 t = *reinterpret_cast<const float4*>(chunk + r * 32 + (((half * 4 + j) ^ (r & 7)) << 2));
+        v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+    }
+}
 __device__ __forceinline__ void load_vec16(float (&v)[16], const float* p) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -211,11 +220,14 @@ __device__ __forceinline__ void load_vec16(float (&v)[16], const float* p) {
 }
 
 // NSETS epilogue sets of four warps: set s handles the 16-column sub-chunks sc with sc % NSETS == s.
-template <int KIND, int NSETS>
-__global__ void __launch_bounds__((4 * NSETS + 3) * 32, 1) tc_edge_kernel(TcArgs a) {
+// (NSETS = 4 was measured no faster than 2; with 4, sets 2-3 never wait on chunk 0 of a tile, whose barrier also
+// publishes S.p / wrow / mrow, so that variant would need an extra wait before it is used.)
+template <int KIND, int NSETS, int NAP>
+__global__ void __launch_bounds__((4 * NSETS + 2 + NAP) * 32, 1) tc_edge_kernel(const __grid_constant__ TcArgs a) {
     constexpr int STAGES = (KIND == TC_UPD) ? 3 : 2;
     constexpr int W_MMA = 4 * NSETS, W_WPROD = 4 * NSETS + 1, W_APROD = 4 * NSETS + 2;
-    constexpr int NTHREADS = (4 * NSETS + 3) * 32, EPI_THREADS = 128 * NSETS;
+    constexpr int NTHREADS = (4 * NSETS + 2 + NAP) * 32, EPI_THREADS = 128 * NSETS;
+    constexpr int RPL = 4 / NAP;                         // tile rows per activation-producer lane
     constexpr int SPT = 8 / NSETS;                       // sub-chunks per thread and stage
     extern __shared__ uint8_t smem_raw[];
     Tc2Smem& S = *reinterpret_cast<Tc2Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -225,7 +237,7 @@ __global__ void __launch_bounds__((4 * NSETS + 3) * 32, 1) tc_edge_kernel(TcArgs
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < T2_NW; ++i) { mbar_init(&S.w_full[i], 1); mbar_init(&S.w_empty[i], 1); }
-        for (int i = 0; i < T2_NACT; ++i) { mbar_init(&S.act_full[i], 64); mbar_init(&S.act_empty[i], 256); }
+        for (int i = 0; i < T2_NACT; ++i) { mbar_init(&S.act_full[i], 64 * NAP); mbar_init(&S.act_empty[i], 256); }
         for (int i = 0; i < 8; ++i) mbar_init(&S.a_ready[i], 128);
         for (int i = 0; i < 2; ++i) mbar_init(&S.d_ready[i], 1);
         fence_barrier_init();
@@ -298,49 +310,53 @@ __global__ void __launch_bounds__((4 * NSETS + 3) * 32, 1) tc_edge_kernel(TcArgs
                     TC_STAMP(g / STAGES, 25 + 2 * l);
                 }
         }
-    } else if (warp == W_APROD) {
-        // ---------------- activation producer ----------------
-        // Every lane owns rows lane, lane+32, lane+64, lane+96 of a tile and copies their 128-byte chunk slices with
-        // eight 16-byte cp.async each (h_E rows, or the neighbour's Q row): no index math inside the copy loop.
+    } else if (warp >= W_APROD) {
+        // ---------------- activation producers (NAP warps) ----------------
+        // Every lane owns RPL rows of a tile (producer warp pw: rows 32 (pw RPL + i) + lane) and copies their 128-byte
+        // chunk slices with eight 16-byte cp.async each (h_E rows, or the neighbour's Q row): no index math inside the
+        // copy loop.  One producer warp sustains only ~1 chunk per 2.2k cycles (each cp.async touches 32 different
+        // lines), which bounded the whole kernel; NAP warps issue in parallel.
+        const int pw = warp - W_APROD;
         // (One 128-byte bulk copy per row was measured 3x slower: too fine-grained for the TMA unit.)
-        // Chunk order = the order the epilogue consumes them: in(0) | q(t), in(t+1), [residual(t)] for t = 0, 1, ...
+        // Chunk order = the order the epilogue consumes them: in(0) | q(t), [residual(t)], in(t+1) for t = 0, 1, ...
         uint32_t k = 0;
-        int jrow[4];
+        int jrow[RPL];
         auto chunk = [&](int row0, int c, bool gather_q, int with_p_buf) {
             const uint32_t s = k % T2_NACT, u = k / T2_NACT;
             if (u > 0) mbar_wait(&S.act_empty[s], (u - 1) & 1);
+            const bool tma_lane = !gather_q && pw == 0 && lane == 0;
+            if (gather_q) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int r = lane + 32 * i;
-                float* dst = &S.act[s][r * ACT_PITCH];
-                if (gather_q || row0 + r < total_rows) {
-                    const float* src = gather_q ? a.Q + (size_t)jrow[i] * a.q_stride + c * 32
-                                                : a.hE + (size_t)(row0 + r) * HID + c * 32;
+                for (int i = 0; i < RPL; ++i) {
+                    const int r = lane + 32 * (pw * RPL + i);
+                    float* dst = &S.act[s][r * ACT_PITCH];
+                    const float* src = a.Q + (size_t)jrow[i] * a.q_stride + c * 32;
 #pragma unroll
                     for (int q = 0; q < 8; ++q) cp_async16_ca(dst + q * 4, src + q * 4);
-                } else {                                   // row past the end of the edge array
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) reinterpret_cast<float4*>(dst)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
+            } else if (tma_lane) {
+                // h_E rows of a tile are contiguous: ONE tensor-map copy per chunk (rows past the end arrive as zeros)
+                mbar_arrive_expect_tx(&S.act_full[s], TC_ROWS * 32 * 4);
+                tma_load_2d(S.act[s], &a.tm_hE, c * 32, row0, &S.act_full[s]);
             }
             if (with_p_buf >= 0) {
                 const int node_lo = row0 / KNB;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = pw * RPL; i < (pw + 1) * RPL; ++i) {
                     int node = node_lo + i; node = node < N ? node : N - 1;
                     cp_async16_ca(&S.p[with_p_buf][i][lane * 4], a.P + (size_t)node * a.p_stride + lane * 4);
                 }
             }
             cp_async_arrive_noinc(&S.act_full[s]);          // fires when this lane's copies have landed
-            mbar_arrive(&S.act_full[s]);                    // releases this lane's plain stores (zeros, wrow/mrow)
+            if (!tma_lane) mbar_arrive(&S.act_full[s]);     // releases this lane's plain stores (wrow/mrow)
             ++k;
         };
         // metadata of a tile (weights / masks per row) + its four input chunks; returns the neighbour rows in jnext
-        auto tile_input = [&](int tile, uint32_t mb, int (&jnext)[4]) {
+        auto tile_input = [&](int tile, uint32_t mb, int (&jnext)[RPL]) {
             const int row0 = tile * TC_ROWS;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int r = lane + 32 * i, row = row0 + r;
+            for (int i = 0; i < RPL; ++i) {
+                const int r = lane + 32 * (pw * RPL + i), row = row0 + r;
                 int j = N - 1;
                 float w = 0.f, mi = 0.f;
                 if (row < total_rows) {
@@ -360,13 +376,13 @@ __global__ void __launch_bounds__((4 * NSETS + 3) * 32, 1) tc_edge_kernel(TcArgs
         for (; tile < num_tiles; tile += gridDim.x, ++ti) {
             const int row0 = tile * TC_ROWS;
             for (int c = 0; c < 4; ++c) chunk(row0, c, true, -1);
-            int jn[4] = {0, 0, 0, 0};
+            if (KIND == TC_UPD)                              // residual BEFORE the next tile's input: it waits in the ring for
+                for (int c = 0; c < 4; ++c) chunk(row0, c, false, -1);   // the LayerNorm pass, which then frees the slots
+            int jn[RPL] = {};
             const int next = tile + gridDim.x;
             if (next < num_tiles) tile_input(next, (ti + 1) & 1, jn);
-            if (KIND == TC_UPD)
-                for (int c = 0; c < 4; ++c) chunk(row0, c, false, -1);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) jrow[i] = jn[i];
+            for (int i = 0; i < RPL; ++i) jrow[i] = jn[i];
         }
         cp_async_wait<0>();
     } else {
@@ -380,15 +396,20 @@ __global__ void __launch_bounds__((4 * NSETS + 3) * 32, 1) tc_edge_kernel(TcArgs
             mbar_wait(&S.act_full[s], (k / T2_NACT) & 1);
             return S.act[s];
         };
-        auto act_release = [&](uint32_t k) { mbar_arrive(&S.act_empty[k % T2_NACT]); };
+        // the slot's next writer may be the TMA unit (async proxy): our ld.shared must be ordered before it
+        // (not needed after reading an input chunk: the slot's next writer is the cp.async gather of q)
+        auto act_release = [&](uint32_t k, bool next_is_tma = true) {
+            if (next_is_tma) fence_proxy_async();
+            mbar_arrive(&S.act_empty[k % T2_NACT]);
+        };
         // input stage of a tile: its four h_E chunks -> A (each thread converts its 16-column half of every chunk)
         auto input_stage = [&]() {
             for (int c = 0; c < SPT; ++c) {
                 const int sc = set + NSETS * c;
                 const float* chunk = act_wait(kc + (sc >> 1));
                 float v[16];
-                load_act16(v, chunk, r, sc & 1);
-                act_release(kc + (sc >> 1));
+                load_act16_sw(v, chunk, r, sc & 1);
+                act_release(kc + (sc >> 1), false);
                 publish_A16(lane_addr, sc, v, &S.a_ready[sc]);
             }
             kc += 4;
@@ -463,8 +484,10 @@ __global__ void __launch_bounds__((4 * NSETS + 3) * 32, 1) tc_edge_kernel(TcArgs
             EPI_STAMP(KIND == TC_UPD ? 6 : 4);
             const uint32_t dcol = (g & 1) ? COL_D1 : COL_D0;
             ++g;
-            if (tile + (int)gridDim.x < num_tiles) input_stage();
-            EPI_STAMP(1);
+            if (KIND != TC_UPD) {
+                if (tile + (int)gridDim.x < num_tiles) input_stage();
+                EPI_STAMP(1);
+            }
             if (KIND == TC_UPD) {
                 // ---- final: + b13 + residual, LayerNorm over the row (two threads per row), direct 64-byte row stores
                 float shift = 0.f, s1 = 0.f, s2 = 0.f;
@@ -474,7 +497,7 @@ __global__ void __launch_bounds__((4 * NSETS + 3) * 32, 1) tc_edge_kernel(TcArgs
                     tmem_ld16(lane_addr + dcol + sc * 16, acc);
                     const float* chunk = act_wait(kc + (sc >> 1));
                     float old[16], bv[16];
-                    load_act16(old, chunk, r, sc & 1);
+                    load_act16_sw(old, chunk, r, sc & 1);
                     act_release(kc + (sc >> 1));
                     load_vec16(bv, &S.vec[1][sc * 16]);
                     tmem_wait_ld();
@@ -496,6 +519,10 @@ __global__ void __launch_bounds__((4 * NSETS + 3) * 32, 1) tc_edge_kernel(TcArgs
                 const float mean_a = shift + s1 * (1.0f / MV);
                 const float m2_a = fmaxf(s2 - s1 * s1 * (1.0f / MV), 0.f);
                 S.lnx[set][r] = make_float2(mean_a, m2_a);
+                if (set == 0) EPI_STAMP(8);
+                // the residual chunks are consumed: the ring refills with the next tile's input while we convert it
+                if (tile + (int)gridDim.x < num_tiles) input_stage();
+                EPI_STAMP(1);
                 named_bar(3, EPI_THREADS);
                 float mean = 0.f, m2 = 0.f;
 #pragma unroll
@@ -868,14 +895,51 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tc_edge_feat_kernel(TcFeatArgs 
     if (warp == 8) tmem_dealloc<512>(tmem);
 }
 
-constexpr int UPD_SETS = 4, MSG_SETS = 4;   // epilogue sets (4 warps each) per kernel kind
+// Tensor map of h_E for the activation producers.  cuTensorMapEncodeTiled is a driver entry point, fetched through the
+// runtime so the library needs no link-time libcuda.  The last encoding is cached per thread (one context per thread).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode_tiled = nullptr;
+static thread_local cudaError_t t_tc_error = cudaSuccess;
+
+cudaError_t tc_take_error() { cudaError_t e = t_tc_error; t_tc_error = cudaSuccess; return e; }
+
+static bool hE_tensor_map(CUtensorMap* out, const float* hE, long long rows) {
+    static thread_local const float* c_ptr = nullptr;
+    static thread_local long long c_rows = -1;
+    static thread_local CUtensorMap c_map;
+    if (c_ptr != hE || c_rows != rows) {
+        if (!g_encode_tiled) return false;
+        const cuuint64_t dims[2] = {(cuuint64_t)HID, (cuuint64_t)rows};
+        const cuuint64_t strides[1] = {(cuuint64_t)HID * sizeof(float)};
+        const cuuint32_t box[2] = {32, (cuuint32_t)TC_ROWS};
+        const cuuint32_t estr[2] = {1, 1};
+        if (g_encode_tiled(&c_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(hE), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
+        c_ptr = hE; c_rows = rows;
+    }
+    *out = c_map;
+    return true;
+}
+
+constexpr int UPD_SETS = 2, MSG_SETS = 2;   // epilogue sets (4 warps each) per kernel kind
+constexpr int UPD_NAP = 4, MSG_NAP = 4;     // activation-producer warps
 
 cudaError_t tc_kernels_init() {
     cudaError_t e;
+    {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if ((e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres)) != cudaSuccess) return e;
+        if (qres != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
+        g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+    }
     const int bytes = (int)sizeof(Tc2Smem) + 1024;
-    if ((e = cudaFuncSetAttribute(tc_edge_kernel<TC_UPD, UPD_SETS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(tc_edge_kernel<TC_ENC, MSG_SETS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(tc_edge_kernel<TC_DEC, MSG_SETS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(tc_edge_kernel<TC_UPD, UPD_SETS, UPD_NAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(tc_edge_kernel<TC_ENC, MSG_SETS, MSG_NAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(tc_edge_kernel<TC_DEC, MSG_SETS, MSG_NAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
     return cudaFuncSetAttribute(tc_edge_feat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcFeatSmem) + 1024);
 }
 
@@ -893,6 +957,8 @@ void launch_tc_edge_feat(const float* atoms, const int* E_idx, const float* D_nb
 static TcArgs tc_args(float* hE, const int* E_idx, const float* P, int p_stride, const float* Q, int q_stride, const float* maskf,
                       const float* wimg, int N) {
     TcArgs a{};
+    if (N <= 0) return a;
+    if (!hE_tensor_map(&a.tm_hE, hE, (long long)N * KNB)) { t_tc_error = cudaErrorInvalidValue; a.N = 0; a.num_tiles = 0; return a; }
     a.hE = hE; a.E_idx = E_idx; a.P = P; a.p_stride = p_stride; a.Q = Q; a.q_stride = q_stride; a.maskf = maskf;
     a.wimg = reinterpret_cast<const uint8_t*>(wimg);
     a.N = N;
@@ -904,19 +970,21 @@ void launch_tc_edge_upd(float* hE, const int* E_idx, const float* P, const float
                         const float* b12, const float* b13, const float* ln_g, const float* ln_b, int N, int sms, cudaStream_t st,
                         long long* trace) {
     TcArgs a = tc_args(hE, E_idx, P, HID, Q, HID, maskf, wimg, N);
+    if (a.num_tiles == 0) return;
     a.v0 = b12; a.v1 = b13; a.v2 = ln_g; a.v3 = ln_b; a.trace = trace;
     const int grid = a.num_tiles < sms ? a.num_tiles : sms;
-    tc_edge_kernel<TC_UPD, UPD_SETS><<<grid, (4 * UPD_SETS + 3) * 32, sizeof(Tc2Smem) + 1024, st>>>(a);
+    tc_edge_kernel<TC_UPD, UPD_SETS, UPD_NAP><<<grid, (4 * UPD_SETS + 2 + UPD_NAP) * 32, sizeof(Tc2Smem) + 1024, st>>>(a);
 }
 
 void launch_tc_msg(bool dec, const float* hE, const int* E_idx, const float* P, int p_stride, const float* Q, int q_stride,
                    const float* maskf, const float* wimg, const float* b2, float* Spart, int N, int sms, cudaStream_t st,
                    long long* trace) {
     TcArgs a = tc_args(const_cast<float*>(hE), E_idx, P, p_stride, Q, q_stride, maskf, wimg, N);
+    if (a.num_tiles == 0) return;
     a.v0 = b2; a.Spart = Spart; a.trace = trace;
     const int grid = a.num_tiles < sms ? a.num_tiles : sms;
-    if (dec) tc_edge_kernel<TC_DEC, MSG_SETS><<<grid, (4 * MSG_SETS + 3) * 32, sizeof(Tc2Smem) + 1024, st>>>(a);
-    else tc_edge_kernel<TC_ENC, MSG_SETS><<<grid, (4 * MSG_SETS + 3) * 32, sizeof(Tc2Smem) + 1024, st>>>(a);
+    if (dec) tc_edge_kernel<TC_DEC, MSG_SETS, MSG_NAP><<<grid, (4 * MSG_SETS + 2 + MSG_NAP) * 32, sizeof(Tc2Smem) + 1024, st>>>(a);
+    else tc_edge_kernel<TC_ENC, MSG_SETS, MSG_NAP><<<grid, (4 * MSG_SETS + 2 + MSG_NAP) * 32, sizeof(Tc2Smem) + 1024, st>>>(a);
 }
 
 }  // namespace tmpnn
