@@ -320,19 +320,27 @@ __global__ void __launch_bounds__((4 * NSETS + 2 + NAP) * 32, 1) tc_edge_kernel(
         // (One 128-byte bulk copy per row was measured 3x slower: too fine-grained for the TMA unit.)
         // Chunk order = the order the epilogue consumes them: in(0) | q(t), [residual(t)], in(t+1) for t = 0, 1, ...
         uint32_t k = 0;
-        int jrow[RPL];
+        int jrow[RPL];                                       // neighbour of the row this lane owns (row 32 (pw RPL + i) + lane)
+        int jq[RPL][8];                                      // neighbour of row 32 (pw RPL + i) + 4 t + lane / 8 (gather pattern)
+        auto spread_j = [&]() {
+#pragma unroll
+            for (int i = 0; i < RPL; ++i)
+#pragma unroll
+                for (int t = 0; t < 8; ++t) jq[i][t] = __shfl_sync(0xffffffffu, jrow[i], 4 * t + (lane >> 3));
+        };
         auto chunk = [&](int row0, int c, bool gather_q, int with_p_buf) {
             const uint32_t s = k % T2_NACT, u = k / T2_NACT;
             if (u > 0) mbar_wait(&S.act_empty[s], (u - 1) & 1);
             const bool tma_lane = !gather_q && pw == 0 && lane == 0;
             if (gather_q) {
+                // eight lanes per 128-byte row slice, four rows per instruction: 4 L1 wavefronts per cp.async instead of
+                // the 32 of a lane-per-row pattern (the LSU data pipe was the busiest unit of the kernel, ncu: 65-70 %)
 #pragma unroll
                 for (int i = 0; i < RPL; ++i) {
-                    const int r = lane + 32 * (pw * RPL + i);
-                    float* dst = &S.act[s][r * ACT_PITCH];
-                    const float* src = a.Q + (size_t)jrow[i] * a.q_stride + c * 32;
+                    float* dst = &S.act[s][(32 * (pw * RPL + i) + (lane >> 3)) * ACT_PITCH + (lane & 7) * 4];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) cp_async16_ca(dst + q * 4, src + q * 4);
+                    for (int t = 0; t < 8; ++t)
+                        cp_async16_ca(dst + 4 * t * ACT_PITCH, a.Q + (size_t)jq[i][t] * a.q_stride + c * 32 + (lane & 7) * 4);
                 }
             } else if (tma_lane) {
                 // h_E rows of a tile are contiguous: ONE tensor-map copy per chunk (rows past the end arrive as zeros)
@@ -375,6 +383,7 @@ __global__ void __launch_bounds__((4 * NSETS + 2 + NAP) * 32, 1) tc_edge_kernel(
         if (tile < num_tiles) tile_input(tile, 0, jrow);
         for (; tile < num_tiles; tile += gridDim.x, ++ti) {
             const int row0 = tile * TC_ROWS;
+            spread_j();
             for (int c = 0; c < 4; ++c) chunk(row0, c, true, -1);
             if (KIND == TC_UPD)                              // residual BEFORE the next tile's input: it waits in the ring for
                 for (int c = 0; c < 4; ++c) chunk(row0, c, false, -1);   // the LayerNorm pass, which then frees the slots
