@@ -323,25 +323,43 @@ def run_ours(args, rank, world, local_rank):
             kern[k] = {"us_per_launch": 1e3 * per_launch_ms, "launches_per_step": n // prof_steps, "share": ms / tot,
                        "algo_tflops": (fe * n_edges + fn * N) / (per_launch_ms * 1e-3) / 1e12,
                        "algo_gbs": (be * n_edges + bn * N) / (per_launch_ms * 1e-3) / 1e9}
-        edge_kernels = [k for k in kern if (k[3:] if k.startswith("tc_") else k) in ("edge_upd", "enc_msg", "dec_msg", "edge_feat")]
-        top = max(edge_kernels, key=lambda k: prof[k][0])
-        tk = kern[top]
-        tensor_core = top.startswith("tc_")
-        traffic = None
+        traffic_tab = {}
         tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get(args.workload, {}).get(top)
-        roofline = {"kernel": top, "bound": "tensor", "achieved": tk["algo_tflops"], "peak": peaks["bf16_tflops"],
-                    "unit": "TFLOP/s", "frac": tk["algo_tflops"] / peaks["bf16_tflops"], "traffic": traffic,
-                    "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture "
-                                    "(profiles/r01_ncu_tc_edge_kernels_c3.md); null when no capture exists for this workload",
-                    "peak_source": peaks["source"] + ", dense bf16 burst",
-                    "note": ("tcgen05 kind::tf32 with the 3xTF32 split (fp32-accurate): 3 tensor-core MACs per algorithmic MAC at half "
-                             "the bf16 rate, so frac <= 1/6 of the dense bf16 peak by construction; achieved counts the reference "
-                             "formulation's FLOPs (SURVEY 8d), the kernel executes fewer (h_V projections hoisted per residue)")
-                            if tensor_core else "FP32 SIMT generation (TMPNN_TC=0)",
-                    "hbm": {"achieved": tk["algo_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": tk["algo_gbs"] / peaks["hbm_gbs"]},
-                    "us_per_launch": tk["us_per_launch"], "share_of_step": tk["share"]}
+            traffic_tab = json.load(open(tp)).get(args.workload, {})
+
+        def roof(k):
+            tk = kern[k]
+            base = k[3:] if k.startswith("tc_") else k
+            if k.startswith("tc_"):
+                note = ("tcgen05 kind::tf32 with the 3xTF32 split (fp32-accurate): 3 tensor-core MACs per algorithmic MAC at half "
+                        "the bf16 rate, so frac <= 1/6 of the dense bf16 peak by construction; achieved counts the reference "
+                        "formulation's FLOPs (SURVEY 8d), the kernel executes fewer (h_V projections hoisted per residue)")
+            elif base in ("node_update", "head"):
+                note = ("FP32 CUDA-core kernel (per-residue GEMVs against L2-resident weights); batch-invariant summation order is "
+                        "part of its contract, so it is not on the tensor cores; frac is against the dense bf16 tensor peak")
+            else:
+                note = "FP32 / integer SIMT kernel"
+            flops = ALGO[base][0] * n_edges + ALGO[base][1] * N
+            r = {"kernel": k, "bound": "tensor" if flops else "hbm", "us_per_launch": tk["us_per_launch"], "share_of_step": tk["share"],
+                 "traffic": traffic_tab.get(k),
+                 "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture "
+                                 "(profiles/, see profiles/r01_traffic.json); null when no capture exists for this workload",
+                 "note": note}
+            if flops:
+                r.update({"achieved": tk["algo_tflops"], "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                          "frac": tk["algo_tflops"] / peaks["bf16_tflops"], "peak_source": peaks["source"] + ", dense bf16 burst",
+                          "hbm": {"achieved": tk["algo_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": tk["algo_gbs"] / peaks["hbm_gbs"]}})
+            else:
+                r.update({"achieved": tk["algo_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": tk["algo_gbs"] / peaks["hbm_gbs"],
+                          "peak_source": peaks["source"] + ", HBM copy burst"})
+            return r
+
+        top = max(kern, key=lambda k: prof[k][0])                 # the kernel with the largest share of the step
+        roofline = roof(top)
+        edge_kernels = [k for k in kern if (k[3:] if k.startswith("tc_") else k) in ("edge_upd", "enc_msg", "dec_msg", "edge_feat")]
+        top_edge = max(edge_kernels, key=lambda k: prof[k][0])
+        roofline["top_edge_kernel"] = roof(top_edge) if top_edge != top else None
         # cpu baseline on a bounded sample (rank 0, N=1 only)
         cpu = None
         if world == 1 and not args.no_cpu:

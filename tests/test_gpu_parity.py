@@ -101,6 +101,16 @@ def test_ragged_batch_equals_single_runs(gpu_model):
         assert np.array_equal(a, b)
 
 
+def test_large_batch_equals_single_runs(gpu_model):
+    """Same definition at a size that takes the large-batch kernel forms (many tiles per SM in the edge kernels, the
+    32-residue node-update blocks): 12 000 residues in one call, spot-checked bit for bit against single-protein calls."""
+    pdbs = [synth(300, 500 + i) for i in range(36)] + [synth(150 + 37 * i, 900 + i) for i in range(6)]
+    assert sum(len(p["seq"]) for p in pdbs) >= 2 * 148 * 32
+    batch = gpu_model.head_tables(pdbs)
+    for i in (0, 17, 35, 36, 41):
+        assert np.array_equal(batch[i], gpu_model.head_tables([pdbs[i]])[0]), i
+
+
 def test_against_oracle_on_fresh_inputs(gpu_model, oracle_weights):
     """Inputs with no committed fixture: the oracle is the checker (edge cases: tiny, K=L, gaps, two chains)."""
     from oracle import thermompnn_oracle as O

@@ -98,6 +98,81 @@ __device__ __forceinline__ void phase_4mat(float (&acc)[NT], StepStream& ws, con
     }
 }
 
+// ---- register-tiled form of the same arithmetic for the step kernel (NT = 16 or 32) ------------------------------------
+// A group's warp covers 16 residues x 32 columns.  step_fma gives every lane one column and all 16 residues: each
+// x value is then fetched by a broadcast LDS.128 that moves 16 useful bytes per shared-memory wavefront, and ncu showed
+// the kernel bound by exactly that (l1tex data-pipe wavefronts 71 %).  Here lane = (hq = lane / 8, pq = lane % 8) owns
+// residues {hq, hq+4, hq+8, ...} (RI of them) and columns [32 w + 4 pq, +4): per four k, 4 weight + 4 x loads of one wavefront
+// each feed 64 FMAs (2.5x fewer wavefronts).  Every (residue, column) still runs the identical k-sequential fmaf chain,
+// so results equal step_fma's bit for bit.  Row pitches 132 / 516 keep the four residues of a load in different banks.
+constexpr int XP = HID + 4, HIDP = 4 * HID + 4;
+
+template <int RI>
+__device__ __forceinline__ void tile_fma(float (&acc)[RI][4], const float* __restrict__ W, const float* __restrict__ x, int ldx,
+                                         int hq, int c0) {
+#pragma unroll
+    for (int kk = 0; kk < WCHUNK_K; kk += 4) {
+        const float4 w0 = *reinterpret_cast<const float4*>(W + kk * HID + c0);
+        const float4 w1 = *reinterpret_cast<const float4*>(W + (kk + 1) * HID + c0);
+        const float4 w2 = *reinterpret_cast<const float4*>(W + (kk + 2) * HID + c0);
+        const float4 w3 = *reinterpret_cast<const float4*>(W + (kk + 3) * HID + c0);
+#pragma unroll
+        for (int i = 0; i < RI; ++i) {
+            const float4 xv = *reinterpret_cast<const float4*>(x + (hq + 4 * i) * ldx + kk);
+            acc[i][0] = fmaf(xv.x, w0.x, acc[i][0]); acc[i][0] = fmaf(xv.y, w1.x, acc[i][0]);
+            acc[i][0] = fmaf(xv.z, w2.x, acc[i][0]); acc[i][0] = fmaf(xv.w, w3.x, acc[i][0]);
+            acc[i][1] = fmaf(xv.x, w0.y, acc[i][1]); acc[i][1] = fmaf(xv.y, w1.y, acc[i][1]);
+            acc[i][1] = fmaf(xv.z, w2.y, acc[i][1]); acc[i][1] = fmaf(xv.w, w3.y, acc[i][1]);
+            acc[i][2] = fmaf(xv.x, w0.z, acc[i][2]); acc[i][2] = fmaf(xv.y, w1.z, acc[i][2]);
+            acc[i][2] = fmaf(xv.z, w2.z, acc[i][2]); acc[i][2] = fmaf(xv.w, w3.z, acc[i][2]);
+            acc[i][3] = fmaf(xv.x, w0.w, acc[i][3]); acc[i][3] = fmaf(xv.y, w1.w, acc[i][3]);
+            acc[i][3] = fmaf(xv.z, w2.w, acc[i][3]); acc[i][3] = fmaf(xv.w, w3.w, acc[i][3]);
+        }
+    }
+}
+
+// phase_ksplit with the tiled inner loop (NT = 4 RI residues): same partials, same combine order.
+// `part` may alias the input rows (the FFN hidden layer): a barrier separates the last read from the first write.
+template <int RI>
+__device__ __forceinline__ void phase_ksplit_t(float (&res)[RI], StepStream& ws, int steps, const float* xin, int ldx, float* part) {
+    constexpr int NT = 4 * RI;
+    const int q = threadIdx.x >> 7, n = threadIdx.x & 127, lane = n & 31;
+    const int hq = lane >> 3, c0 = (n & 96) + 4 * (lane & 7);
+    float acc[RI][4];
+#pragma unroll
+    for (int i = 0; i < RI; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
+    for (int s = 0; s < steps; ++s) {
+        const float* W = ws.next() + q * WCHUNK_FLOATS;
+        tile_fma<RI>(acc, W, xin + (q * steps + s) * WCHUNK_K, ldx, hq, c0);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < RI; ++i)
+        *reinterpret_cast<float4*>(part + (q * NT + hq + 4 * i) * HID + c0) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < RI; ++j) {
+        const int t = q + 4 * j;
+        res[j] = (part[t * HID + n] + part[(NT + t) * HID + n]) + (part[(2 * NT + t) * HID + n] + part[(3 * NT + t) * HID + n]);
+    }
+}
+
+// phase_4mat with the tiled inner loop: acc[i][c] = (matrix q . x)[residue hq + 4 i][column c0 + c]
+template <int RI>
+__device__ __forceinline__ void phase_4mat_t(float (&acc)[RI][4], StepStream& ws, const float* xin, int ldx, int hq, int c0) {
+    const int q = threadIdx.x >> 7;
+#pragma unroll
+    for (int i = 0; i < RI; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
+    for (int s = 0; s < 4; ++s) {
+        const float* W = ws.next() + q * WCHUNK_FLOATS;
+        tile_fma<RI>(acc, W, xin + s * WCHUNK_K, ldx, hq, c0);
+    }
+}
+
 // LayerNorm over the 128 columns held by the four warps of a group.  Block-wide barriers inside.
 template <int NJ>
 __device__ __forceinline__ void group_layernorm(float (&v)[NJ], const float* __restrict__ g, const float* __restrict__ b,
@@ -330,12 +405,14 @@ __global__ void __launch_bounds__(NK_THREADS, 1) node_update_step_kernel(NodeUpd
     constexpr int NJ = NT / 4;
     extern __shared__ __align__(16) float smem[];
     float* ring = smem;                              // [2][4][4096]
-    float* x = ring + 2 * STEP_FLOATS;               // [NT][128]
-    float* hid = x + NT * HID;                       // [NT][512]
-    float* part = hid + NT * 4 * HID;                // [4][NT][128]
-    float* red = part + 4 * NT * HID;                // [16][NJ]
+    static_assert(NT == 16 || NT == 32, "four residues per lane group and tile row");
+    float* x = ring + 2 * STEP_FLOATS;               // [NT][XP]    (padded rows, see tile_fma)
+    float* hid = x + NT * XP;                        // [NT][HIDP]
+    float* part = hid;                               // [4][NT][128] K-split partials, aliasing the hidden layer
+    float* red = hid + NT * HIDP;                    // [16][NJ]
     float* cnt_s = red + 16 * NJ;                    // [NT]
     const int q = threadIdx.x >> 7, n = threadIdx.x & 127;
+    const int hq = (n & 31) >> 3, c0 = (n & 96) + 4 * (n & 7);       // this thread's residues {hq + 4 i} and columns [c0, c0 + 4)
     const int node0 = blockIdx.x * NT;
     const float* wb = a.weights;
     StepStream ws;
@@ -348,10 +425,10 @@ __global__ void __launch_bounds__(NK_THREADS, 1) node_update_step_kernel(NodeUpd
                 const float* sp = a.Spart + (size_t)node * 3 * HID + c;
                 s = (sp[0] + sp[HID]) + sp[2 * HID];
             }
-            x[i] = s;
+            x[(i / HID) * XP + c] = s;
         }
-        if (threadIdx.x < NT * 32) {
-            const int t = threadIdx.x >> 5, lane = threadIdx.x & 31, node = node0 + t;
+        for (int t = threadIdx.x >> 5; t < NT; t += NK_THREADS / 32) {   // one warp per residue
+            const int lane = threadIdx.x & 31, node = node0 + t;
             float c = 0.f;
             if (node < a.N) {
                 const float mi = a.maskf[node];
@@ -367,12 +444,12 @@ __global__ void __launch_bounds__(NK_THREADS, 1) node_update_step_kernel(NodeUpd
     } else {
         for (int i = threadIdx.x; i < NT * HID; i += NK_THREADS) {
             int node = node0 + i / HID;
-            x[i] = node < a.N ? a.Ssum[(size_t)node0 * HID + i] : 0.f;
+            x[(i / HID) * XP + i % HID] = node < a.N ? a.Ssum[(size_t)node0 * HID + i] : 0.f;
         }
         if (threadIdx.x < NT) cnt_s[threadIdx.x] = (node0 + threadIdx.x < a.N) ? a.cnt[node0 + threadIdx.x] : 0.f;
     }
     float res[NJ], h[NJ];
-    phase_ksplit<NT>(res, ws, 1, x, HID, part);                       // W3
+    phase_ksplit_t<NJ>(res, ws, 1, x, XP, part);                           // W3
     {
         const float b3 = __ldg(wb + a.w.b3 + n);
 #pragma unroll
@@ -384,15 +461,17 @@ __global__ void __launch_bounds__(NK_THREADS, 1) node_update_step_kernel(NodeUpd
     }
     group_layernorm<NJ>(h, wb + a.w.n1.g, wb + a.w.n1.b, red);
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) x[(q + 4 * j) * HID + n] = h[j];
+    for (int j = 0; j < NJ; ++j) x[(q + 4 * j) * XP + n] = h[j];
     {   // FFN 128 -> 512: group q owns hidden columns [128 q, 128 q + 128)
-        float acc[NT];
-        phase_4mat<NT>(acc, ws, x, HID);
-        const float bi = __ldg(wb + a.w.bin + q * HID + n);
+        float acc[NJ][4];
+        phase_4mat_t<NJ>(acc, ws, x, XP, hq, c0);
+        const float4 bi = __ldg(reinterpret_cast<const float4*>(wb + a.w.bin + q * HID + c0));
 #pragma unroll
-        for (int t = 0; t < NT; ++t) hid[t * 4 * HID + q * HID + n] = gelu_erf(acc[t] + bi);
+        for (int i = 0; i < NJ; ++i)
+            *reinterpret_cast<float4*>(hid + (hq + 4 * i) * HIDP + q * HID + c0) =
+                make_float4(gelu_erf(acc[i][0] + bi.x), gelu_erf(acc[i][1] + bi.y), gelu_erf(acc[i][2] + bi.z), gelu_erf(acc[i][3] + bi.w));
     }
-    phase_ksplit<NT>(res, ws, 4, hid, 4 * HID, part);                  // FFN 512 -> 128
+    phase_ksplit_t<NJ>(res, ws, 4, hid, HIDP, part);                       // FFN 512 -> 128
     {
         const float bo = __ldg(wb + a.w.bout + n);
 #pragma unroll
@@ -404,25 +483,28 @@ __global__ void __launch_bounds__(NK_THREADS, 1) node_update_step_kernel(NodeUpd
         const int t = q + 4 * j, node = node0 + t;
         const float m = node < a.N ? a.maskf[node] : 0.f;
         h[j] *= m;
-        x[t * HID + n] = h[j];
+        x[t * XP + n] = h[j];
         if (node < a.N) {
             a.hV[(size_t)node * HID + n] = h[j];
             if (a.hV_copy) a.hV_copy[(size_t)node * HID + n] = h[j];
         }
     }
     if (a.nproj > 0) {                                                 // group q computes projection q (idle if q >= nproj)
-        float acc[NT];
-        phase_4mat<NT>(acc, ws, x, HID);
+        float acc[NJ][4];
+        phase_4mat_t<NJ>(acc, ws, x, XP, hq, c0);
         if (q < a.nproj) {
             const ProjSpec ps = a.proj[q];
-            const float b = ps.bias >= 0 ? __ldg(wb + ps.bias + n) : 0.f;
+            const float4 b = ps.bias >= 0 ? __ldg(reinterpret_cast<const float4*>(wb + ps.bias + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int t = 0; t < NT; ++t) {
-                const int node = node0 + t;
+            for (int i = 0; i < NJ; ++i) {
+                const int node = node0 + hq + 4 * i;
                 if (node < a.N) {
-                    float v = acc[t] + b;
-                    if (ps.table >= 0) v += __ldg(wb + ps.table + (size_t)a.S[node] * HID + n);
-                    ps.out[(size_t)node * HID + n] = v;
+                    float4 v = make_float4(acc[i][0] + b.x, acc[i][1] + b.y, acc[i][2] + b.z, acc[i][3] + b.w);
+                    if (ps.table >= 0) {
+                        const float4 tv = __ldg(reinterpret_cast<const float4*>(wb + ps.table + (size_t)a.S[node] * HID + c0));
+                        v.x += tv.x; v.y += tv.y; v.z += tv.z; v.w += tv.w;
+                    }
+                    *reinterpret_cast<float4*>(ps.out + (size_t)node * HID + c0) = v;
                 }
             }
         }
@@ -490,7 +572,7 @@ template <int NT> static size_t smem_node_update() {
     return sizeof(float) * (NC_RING * WCHUNK_FLOATS + 3 * NT * HID + 16 * (NT / 4) + NT);
 }
 template <int NT> static size_t smem_node_update_step() {
-    return sizeof(float) * (2 * STEP_FLOATS + NT * HID + NT * 4 * HID + 4 * NT * HID + 16 * (NT / 4) + NT);
+    return sizeof(float) * (2 * STEP_FLOATS + NT * XP + NT * HIDP + 16 * (NT / 4) + NT);
 }
 template <int NT> static size_t smem_head() {
     return sizeof(float) * (2 * STEP_FLOATS + 2 * NT * 3 * HID + 4 * NT * HID);
@@ -502,13 +584,15 @@ cudaError_t node_kernels_init() {
     if ((e = cudaFuncSetAttribute(node_update_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_node_update<16>())) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(node_update_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_node_update<12>())) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(node_update_step_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_node_update_step<16>())) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(node_update_step_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_node_update_step<32>())) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(head_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_head<8>())) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
 void launch_node_update(const NodeUpdArgs& a, int sms, cudaStream_t st) {
     // Small batches: a 4-CTA cluster per tile of NT residues, NT chosen so that the whole grid is ONE wave (152 CTAs on
-    // 148 SMs would take two).  Large batches: the single-CTA step kernel, 16 residues per block.
+    // 148 SMs would take two).  Large batches: the single-CTA step kernel, 16 or 32 residues per block.
+    // All forms are bit-identical per residue, so the choice never shows in the results.
     const int N = a.N;
     if (4 * ((N + 7) / 8) <= sms) {
         node_update_kernel<8><<<4 * ((N + 7) / 8), NC_THREADS, smem_node_update<8>(), st>>>(a);
@@ -516,8 +600,10 @@ void launch_node_update(const NodeUpdArgs& a, int sms, cudaStream_t st) {
         node_update_kernel<12><<<4 * ((N + 11) / 12), NC_THREADS, smem_node_update<12>(), st>>>(a);
     } else if (4 * ((N + 15) / 16) <= sms) {
         node_update_kernel<16><<<4 * ((N + 15) / 16), NC_THREADS, smem_node_update<16>(), st>>>(a);
-    } else {
+    } else if ((N + 31) / 32 < 2 * sms) {
         node_update_step_kernel<16><<<(N + 15) / 16, NK_THREADS, smem_node_update_step<16>(), st>>>(a);
+    } else {   // at least two full waves of 32-residue blocks: half the weight traffic per residue
+        node_update_step_kernel<32><<<(N + 31) / 32, NK_THREADS, smem_node_update_step<32>(), st>>>(a);
     }
 }
 

@@ -1,0 +1,115 @@
+#!/usr/bin/env python
+"""Dev tool: turn the raw ncu output of tools/round_artifacts.sh (gpurun_out/<tag>_*) into the committed summaries
+under profiles/ (launch-list tables, --set full metric tables, <tag>_traffic.json, bench lines)."""
+import csv, io, json, os, re, subprocess, sys
+from collections import OrderedDict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+
+KNAMES = {"tc_edge_kernel<0": "tc_edge_upd", "tc_edge_kernel<1": "tc_enc_msg", "tc_edge_kernel<2": "tc_dec_msg",
+          "tc_edge_feat_kernel": "tc_edge_feat", "node_update_step_kernel": "node_update", "node_update_kernel": "node_update",
+          "head_kernel": "head", "knn_kernel": "knn", "prep_nodes_kernel": "prep_nodes"}
+
+
+def short(name):
+    m = re.search(r"(tmpnn::)?([A-Za-z_0-9]+(<[^>(]*>?)?)", name.replace("void ", ""))
+    s = name.replace("void ", "").split("(")[0]
+    return s[:72]
+
+
+def engine_name(kernel):
+    for k, v in KNAMES.items():
+        if k in kernel:
+            return v
+    return None
+
+
+def launch_list(workload, cmd):
+    path = os.path.join(G, f"{tag}_launches_{workload}.csv")
+    if not os.path.exists(path):
+        return
+    lines = [l for l in open(path) if l.startswith('"')]
+    rows = list(csv.DictReader(io.StringIO("".join(lines))))
+    agg = OrderedDict()
+    for r in rows:
+        k = short(r["Kernel Name"])
+        a = agg.setdefault(k, [0, 0.0])
+        a[0] += 1; a[1] += float(r["Metric Value"]) / 1e3
+    tot = sum(v[1] for k, v in agg.items() if "at::" not in k)
+    out = [f"# Round {tag[1:]}: ncu launch list, workload {workload.upper()}", "",
+           f"Command (on the B200 box): `{cmd}`", "",
+           "Per-launch times under ncu are cold-cache and serialised: compare SHARES with bench.py's `kernels` block, not absolutes.",
+           "Shares exclude bench.py's L2-flush fill kernel (`at::...FillFunctor`, outside the timed events).", "",
+           "| kernel | launches | sum us | avg us | share |", "|---|---|---|---|---|"]
+    for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        share = f"{100 * us / tot:.1f}%" if "at::" not in k else "-"
+        out.append(f"| `{k}` | {n} | {us:.1f} | {us / n:.1f} | {share} |")
+    out += ["", "`tc_edge_kernel<0,..>` = edge_upd, `<1,..>` = enc_msg, `<2,..>` = dec_msg (tcgen05)."]
+    bj = os.path.join(G, f"{tag}_bench_{workload}.json")
+    if os.path.exists(bj):
+        d = json.load(open(bj))
+        out += ["", f"bench.py `kernels` block of the un-profiled run (`{tag}_bench_{workload}.json`): CUDA-event time per launch, share of the step:", "",
+                "| kernel | launches/step | us per launch | share |", "|---|---|---|---|"]
+        for k, v in sorted(d["kernels"].items(), key=lambda kv: -kv[1]["share"]):
+            out.append(f"| {k} | {v['launches_per_step']} | {v['us_per_launch']:.1f} | {100 * v['share']:.1f}% |")
+    open(os.path.join(P, f"{tag}_launches_{workload}.md"), "w").write("\n".join(out) + "\n")
+
+
+METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
+           "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor.sum",
+           "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+           "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+           "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+           "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+           "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ldgsts.sum", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum",
+           "lts__t_sector_hit_rate.pct", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+           "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio"]
+
+
+def full_capture(workload, cmd, traffic):
+    rep = os.path.join(G, f"{tag}_full_{workload}.ncu-rep")
+    if not os.path.exists(rep):
+        return
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    col = {h: i for i, h in enumerate(hdr)}
+    names = [short(r[col["Kernel Name"]]) for r in data]
+    out = [f"# Round {tag[1:]}: `ncu --set full`, workload {workload.upper()}", "", f"Command: `{cmd}`", "",
+           "| metric | unit | " + " | ".join(f"`{n[:34]}`" for n in names) + " |", "|---|---|" + "---|" * len(names)]
+    for m in METRICS:
+        if m in col:
+            out.append(f"| {m} | {units[col[m]]} | " + " | ".join(r[col[m]] for r in data) + " |")
+    out.append("")
+    for r, n in zip(data, names):
+        en = engine_name(r[col["Kernel Name"]])
+        def val(m):
+            v = float(r[col[m]].replace(",", "")); u = units[col[m]]
+            return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}.get(u, 1)
+        t = val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
+        if en and en not in traffic.setdefault(workload, {}):
+            traffic[workload][en] = t
+        out.append(f"- `{n[:60]}` ({en}): DRAM read+write per launch = {t / 1e6:.1f} MB")
+    open(os.path.join(P, f"{tag}_ncu_full_{workload}.md"), "w").write("\n".join(out) + "\n")
+
+
+if __name__ == "__main__":
+    launch_list("c2", f"ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/{tag}_launches_c2.csv python bench.py --steps 2 --warmup 3 --no-cpu")
+    launch_list("c3", f"ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/{tag}_launches_c3.csv python bench.py --workload c3 --steps 2 --warmup 3 --no-cpu")
+    traffic = {"note": "dram__bytes_read.sum + dram__bytes_write.sum per launch (bytes), first captured launch of each kernel, from the "
+                       f"ncu --set full captures summarised in profiles/{tag}_ncu_full_c2.md / _c3.md"}
+    full_capture("c3", f"ncu --set full --clock-control none --import-source on -k regex:'tc_edge_kernel|node_update' -s 45 -c 4 -o gpurun_out/{tag}_full_c3 python bench.py --workload c3 --steps 1 --warmup 3 --no-cpu", traffic)
+    full_capture("c2", f"ncu --set full --clock-control none --import-source on -k regex:'tc_edge_kernel|node_update' -s 45 -c 3 -o gpurun_out/{tag}_full_c2 python bench.py --steps 1 --warmup 3 --no-cpu", traffic)
+    json.dump(traffic, open(os.path.join(P, f"{tag}_traffic.json"), "w"), indent=1)
+    lines = []
+    for w in ("c2", "c3", "c5", "ref"):
+        bj = os.path.join(G, f"{tag}_bench_{w}.json")
+        if os.path.exists(bj):
+            lines.append(open(bj).read().strip())
+    open(os.path.join(P, f"{tag}_bench_lines.jsonl"), "w").write("\n".join(lines) + "\n")
+    print("wrote", sorted(f for f in os.listdir(P) if f.startswith(tag)))
