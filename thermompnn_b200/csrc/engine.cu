@@ -623,6 +623,9 @@ int tmpnn_run_batch(tmpnn_ctx* ctx, int32_t B, const int32_t* offsets, const flo
     auto stage_done = [&](int s) { if (stop == s) done = true; return done; };
 
     // ---- pipeline ---------------------------------------------------------------
+    // (h_V starts at zero, protein_mpnn_utils.py:1225; cleared up front so that no memset sits between two kernels
+    // of the programmatic-dependent-launch chain)
+    CU(cudaMemsetAsync(ctx->hV.p, 0, n * HID * sizeof(float), st));
     { LaunchScope ls(ctx, st, "prep_nodes");
       launch_prep_nodes(d_off, B, d_X, d_m, N, ctx->pstart.p, ctx->pend.p, ctx->atoms.p, ctx->maskf.p, st); }
     { LaunchScope ls(ctx, st, "knn");
@@ -637,7 +640,6 @@ int tmpnn_run_batch(tmpnn_ctx* ctx, int32_t B, const int32_t* offsets, const flo
             launch_edge_feat(npt, ctx->atoms.p, ctx->E_idx.p, ctx->D_nb.p, d_r, d_c, W + L.pos_table, W + L.rbf_mu,
                              W + L.feat, W + L.ne.g, W + L.ne.b, W + L.be, ctx->hE.p, N, st);
         }
-        CU(cudaMemsetAsync(ctx->hV.p, 0, n * HID * sizeof(float), st));
     }
     if (!done && !stage_done(2)) {
         for (int l = 0; l < 3 && !done; ++l) {

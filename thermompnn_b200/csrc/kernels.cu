@@ -18,6 +18,7 @@
 //   W1c.W_s[S_j] is a 21-row table per decoder layer.
 #include "common.cuh"
 #include "kernels.h"
+#include "pdl.cuh"
 
 #include <cfloat>
 
@@ -34,6 +35,8 @@ __constant__ int8_t c_pair_b[NPAIR] = {1, 0, 2, 3, 4, 0, 2, 3, 4, 2, 3, 4, 2, 3,
 __global__ void prep_nodes_kernel(const int* __restrict__ offsets, int B, const float* __restrict__ X,
                                   const uint8_t* __restrict__ mask_u8, int N, int* __restrict__ pstart,
                                   int* __restrict__ pend, float* __restrict__ atoms, float* __restrict__ maskf) {
+    pdl_trigger();
+    pdl_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     int lo = 0, hi = B;  // find b with offsets[b] <= i < offsets[b+1]
@@ -71,6 +74,8 @@ __global__ void prep_nodes_kernel(const int* __restrict__ offsets, int B, const 
 __global__ void knn_kernel(const float* __restrict__ atoms, const float* __restrict__ maskf,
                            const int* __restrict__ pstart, const int* __restrict__ pend, int N, int lmax,
                            int* __restrict__ E_idx, float* __restrict__ D_nb) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float s_row[];
     const int warps = blockDim.x >> 5;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -479,7 +484,7 @@ cudaError_t kernels_init() {
 
 void launch_prep_nodes(const int* offsets, int B, const float* X, const uint8_t* mask, int N, int* pstart, int* pend,
                        float* atoms, float* maskf, cudaStream_t st) {
-    prep_nodes_kernel<<<(N + 127) / 128, 128, 0, st>>>(offsets, B, X, mask, N, pstart, pend, atoms, maskf);
+    launch_pdl(prep_nodes_kernel, dim3((N + 127) / 128), dim3(128), 0, st, offsets, B, X, mask, N, pstart, pend, atoms, maskf);
 }
 
 int knn_max_len() { return 200 * 1024 / 4 - 2 * KNB; }
@@ -490,7 +495,7 @@ void launch_knn(const float* atoms, const float* maskf, const int* pstart, const
     const size_t per_warp = (size_t)(lmax + 2 * KNB) * 4;
     while (warps > 1 && (size_t)warps * per_warp > 200 * 1024) warps >>= 1;
     size_t smem = (size_t)warps * per_warp;
-    knn_kernel<<<(N + warps - 1) / warps, warps * 32, smem, st>>>(atoms, maskf, pstart, pend, N, lmax, E_idx, D_nb);
+    launch_pdl(knn_kernel, dim3((N + warps - 1) / warps), dim3(warps * 32), smem, st, atoms, maskf, pstart, pend, N, lmax, E_idx, D_nb);
 }
 
 #define TMPNN_DISPATCH_NPT(npt, CALL)  \

@@ -10,6 +10,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "pdl.cuh"
 
 namespace tmpnn {
 
@@ -266,8 +267,10 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NC_THREADS, 1) node_
         cp_async_commit();
         ++issued;
     };
+    pdl_trigger();
 #pragma unroll
     for (int k = 0; k < NC_RING - 1; ++k) issue();
+    pdl_wait();                                      // weights are constants; everything below reads earlier kernels' output
     auto next_chunk = [&]() -> const float* {       // block-wide; also publishes earlier shared-memory writes
         cp_async_wait<NC_RING - 2>();
         __syncthreads();
@@ -416,7 +419,9 @@ __global__ void __launch_bounds__(NK_THREADS, 1) node_update_step_kernel(NodeUpd
     const int node0 = blockIdx.x * NT;
     const float* wb = a.weights;
     StepStream ws;
+    pdl_trigger();
     ws.start(wb + a.w.stream, ring, a.w.nchunks / 4);
+    pdl_wait();
     if (a.Spart) {
         for (int i = threadIdx.x; i < NT * HID; i += NK_THREADS) {
             const int node = node0 + i / HID, c = i % HID;
@@ -529,7 +534,9 @@ __global__ void __launch_bounds__(NK_THREADS, 1) head_kernel(HeadArgs a) {
     const int node0 = blockIdx.x * NT;
     const float* wb = a.weights;
     StepStream ws;
+    pdl_trigger();
     ws.start(wb + a.stream, ring, 14);
+    pdl_wait();
     for (int i = threadIdx.x; i < NT * HID; i += NK_THREADS) {
         int t = i / HID, c = i % HID, node = node0 + t;
         bool ok = node < a.N;
@@ -595,20 +602,20 @@ void launch_node_update(const NodeUpdArgs& a, int sms, cudaStream_t st) {
     // All forms are bit-identical per residue, so the choice never shows in the results.
     const int N = a.N;
     if (4 * ((N + 7) / 8) <= sms) {
-        node_update_kernel<8><<<4 * ((N + 7) / 8), NC_THREADS, smem_node_update<8>(), st>>>(a);
+        launch_pdl(node_update_kernel<8>, dim3(4 * ((N + 7) / 8)), dim3(NC_THREADS), smem_node_update<8>(), st, a);
     } else if (4 * ((N + 11) / 12) <= sms) {
-        node_update_kernel<12><<<4 * ((N + 11) / 12), NC_THREADS, smem_node_update<12>(), st>>>(a);
+        launch_pdl(node_update_kernel<12>, dim3(4 * ((N + 11) / 12)), dim3(NC_THREADS), smem_node_update<12>(), st, a);
     } else if (4 * ((N + 15) / 16) <= sms) {
-        node_update_kernel<16><<<4 * ((N + 15) / 16), NC_THREADS, smem_node_update<16>(), st>>>(a);
+        launch_pdl(node_update_kernel<16>, dim3(4 * ((N + 15) / 16)), dim3(NC_THREADS), smem_node_update<16>(), st, a);
     } else if ((N + 31) / 32 < 2 * sms) {
-        node_update_step_kernel<16><<<(N + 15) / 16, NK_THREADS, smem_node_update_step<16>(), st>>>(a);
+        launch_pdl(node_update_step_kernel<16>, dim3((N + 15) / 16), dim3(NK_THREADS), smem_node_update_step<16>(), st, a);
     } else {   // at least two full waves of 32-residue blocks: half the weight traffic per residue
-        node_update_step_kernel<32><<<(N + 31) / 32, NK_THREADS, smem_node_update_step<32>(), st>>>(a);
+        launch_pdl(node_update_step_kernel<32>, dim3((N + 31) / 32), dim3(NK_THREADS), smem_node_update_step<32>(), st, a);
     }
 }
 
 void launch_head(const HeadArgs& a, cudaStream_t st) {
-    head_kernel<8><<<(a.N + 7) / 8, NK_THREADS, smem_head<8>(), st>>>(a);
+    launch_pdl(head_kernel<8>, dim3((a.N + 7) / 8), dim3(NK_THREADS), smem_head<8>(), st, a);
 }
 
 }  // namespace tmpnn

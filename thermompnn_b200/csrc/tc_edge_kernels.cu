@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "tc_common.cuh"
+#include "pdl.cuh"
 
 namespace tmpnn {
 
@@ -251,6 +252,10 @@ __global__ void __launch_bounds__((4 * NSETS + 2 + NAP) * 32, 1) tc_edge_kernel(
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = S.tmem_base;
+    // PDL: everything above touched only constants, shared memory and TMEM.  The weight producer keeps to constants and
+    // starts streaming at once; every other warp first waits for the kernels that wrote h_E / P / Q / E_idx.
+    pdl_trigger();
+    if (warp != W_WPROD) pdl_wait();
 
     if (warp == W_WPROD) {
         // ---------------- weight producer ----------------
@@ -683,6 +688,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tc_edge_feat_kernel(TcFeatArgs 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = S.tmem_base;
+    pdl_trigger();                                        // (see tc_edge_kernel)
+    if (warp != 9) pdl_wait();
 
     if (warp == 9) {
         if (lane == 0) {                                  // weight producer
@@ -960,7 +967,7 @@ void launch_tc_edge_feat(const float* atoms, const int* E_idx, const float* D_nb
     a.wimg = reinterpret_cast<const uint8_t*>(wimg); a.ln_g = ln_g; a.ln_b = ln_b; a.b_e = b_e; a.hE = hE; a.N = N;
     a.num_tiles = (N * KNB + TC_ROWS - 1) / TC_ROWS;
     const int grid = a.num_tiles < sms ? a.num_tiles : sms;
-    tc_edge_feat_kernel<<<grid, T2_THREADS, sizeof(TcFeatSmem) + 1024, st>>>(a);
+    launch_pdl(tc_edge_feat_kernel, dim3(grid), dim3(T2_THREADS), sizeof(TcFeatSmem) + 1024, st, a);
 }
 
 static TcArgs tc_args(float* hE, const int* E_idx, const float* P, int p_stride, const float* Q, int q_stride, const float* maskf,
@@ -982,7 +989,7 @@ void launch_tc_edge_upd(float* hE, const int* E_idx, const float* P, const float
     if (a.num_tiles == 0) return;
     a.v0 = b12; a.v1 = b13; a.v2 = ln_g; a.v3 = ln_b; a.trace = trace;
     const int grid = a.num_tiles < sms ? a.num_tiles : sms;
-    tc_edge_kernel<TC_UPD, UPD_SETS, UPD_NAP><<<grid, (4 * UPD_SETS + 2 + UPD_NAP) * 32, sizeof(Tc2Smem) + 1024, st>>>(a);
+    launch_pdl(tc_edge_kernel<TC_UPD, UPD_SETS, UPD_NAP>, dim3(grid), dim3((4 * UPD_SETS + 2 + UPD_NAP) * 32), sizeof(Tc2Smem) + 1024, st, a);
 }
 
 void launch_tc_msg(bool dec, const float* hE, const int* E_idx, const float* P, int p_stride, const float* Q, int q_stride,
@@ -992,8 +999,8 @@ void launch_tc_msg(bool dec, const float* hE, const int* E_idx, const float* P, 
     if (a.num_tiles == 0) return;
     a.v0 = b2; a.Spart = Spart; a.trace = trace;
     const int grid = a.num_tiles < sms ? a.num_tiles : sms;
-    if (dec) tc_edge_kernel<TC_DEC, MSG_SETS, MSG_NAP><<<grid, (4 * MSG_SETS + 2 + MSG_NAP) * 32, sizeof(Tc2Smem) + 1024, st>>>(a);
-    else tc_edge_kernel<TC_ENC, MSG_SETS, MSG_NAP><<<grid, (4 * MSG_SETS + 2 + MSG_NAP) * 32, sizeof(Tc2Smem) + 1024, st>>>(a);
+    if (dec) launch_pdl(tc_edge_kernel<TC_DEC, MSG_SETS, MSG_NAP>, dim3(grid), dim3((4 * MSG_SETS + 2 + MSG_NAP) * 32), sizeof(Tc2Smem) + 1024, st, a);
+    else launch_pdl(tc_edge_kernel<TC_ENC, MSG_SETS, MSG_NAP>, dim3(grid), dim3((4 * MSG_SETS + 2 + MSG_NAP) * 32), sizeof(Tc2Smem) + 1024, st, a);
 }
 
 }  // namespace tmpnn
