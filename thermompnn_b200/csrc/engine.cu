@@ -483,7 +483,7 @@ int tmpnn_create(int device, tmpnn_ctx** out) {
     if ((e = node_kernels_init()) != cudaSuccess) return bail(std::string("node_kernels_init: ") + cudaGetErrorString(e));
     if ((e = tc_kernels_init()) != cudaSuccess) return bail(std::string("tc_kernels_init: ") + cudaGetErrorString(e));
     if (const char* env = std::getenv("TMPNN_TC_TRACE"))
-        if (std::atoi(env)) { cudaMalloc(&ctx->d_trace, 2 * 512 * sizeof(long long)); cudaMemset(ctx->d_trace, 0, 2 * 512 * sizeof(long long)); }
+        if (std::atoi(env)) { cudaMalloc(&ctx->d_trace, 3 * 512 * sizeof(long long)); cudaMemset(ctx->d_trace, 0, 3 * 512 * sizeof(long long)); }
     if (const char* env = std::getenv("TMPNN_TC")) ctx->tc_mask = std::atoi(env) == 1 ? 7 : std::atoi(env);
     *out = ctx;
     return TMPNN_OK;
@@ -662,6 +662,7 @@ int tmpnn_run_batch(tmpnn_ctx* ctx, int32_t B, const int32_t* offsets, const flo
             a.weights = W; a.w = e.nu; a.Ssum = ctx->Ssum.p; a.cnt = ctx->cnt.p; a.hV = ctx->hV.p; a.hV_copy = nullptr;
             a.Spart = (ctx->tc_mask & 2) ? ctx->Spart.p : nullptr; a.E_idx = ctx->E_idx.p; a.enc = 1;
             a.maskf = ctx->maskf.p; a.S = d_S; a.N = N;
+            a.trace = (l == 1 && ctx->d_trace) ? ctx->d_trace + 1024 : nullptr;
             a.proj[0] = {e.b11, -1, ctx->P2.p};     // edge update of this layer
             a.proj[1] = {-1, -1, ctx->Q2.p};
             if (l < 2) {
@@ -748,6 +749,7 @@ int tmpnn_fetch(tmpnn_ctx* ctx, const char* name, void* host_dst, int64_t bytes)
     else if (s == "dec2") { src = ctx->dec_last.p; sz = n * HID * 4; }
     else if (s == "table") { src = ctx->last_table; sz = n * 21 * 4; }
     else if (s == "tc_trace" && ctx->d_trace) { src = ctx->d_trace; sz = 2 * 512 * sizeof(long long); }
+    else if (s == "node_trace" && ctx->d_trace) { src = ctx->d_trace + 1024; sz = 64 * sizeof(long long); }
     else return fail(ctx, TMPNN_E_NOTFOUND, "tmpnn_fetch: unknown tensor '" + s + "'");
     if ((size_t)bytes != sz)
         return fail(ctx, TMPNN_E_RANGE, "tmpnn_fetch: '" + s + "' is " + std::to_string(sz) + " bytes, caller gave " + std::to_string(bytes));

@@ -28,6 +28,7 @@ struct NodeUpdArgs {
     ProjSpec proj[4];
     int nproj;
     int N;
+    long long* trace;    // optional (TMPNN_TC_TRACE=1, dev tool): clock64() phase stamps of cluster 0, CTA 0
 };
 
 struct HeadArgs {

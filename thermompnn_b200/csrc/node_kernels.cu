@@ -214,8 +214,8 @@ __device__ __forceinline__ void group_layernorm(float (&v)[NJ], const float* __r
 // node_update:  dh = (W3.Ssum + cnt*b3)/30 ; h = LN1(h_V + dh) ; h = LN2(h + FFN(h)) ; h *= mask
 // (protein_mpnn_utils.py:826-832, 871-880), then the projections the next kernels gather.
 //
-// A tile of NT residues is handled by a CLUSTER of four CTAs.  CTA q streams only chunk q of every step (a quarter of
-// the 0.8 MB), through a 6-deep cp.async ring:
+// A tile of NT residues is handled by a CLUSTER of four CTAs.  CTA q loads only chunk q of every step (a quarter of
+// the 0.8 MB) and keeps it resident (nine chunks requested at once, before the dependency wait; projections reuse slots):
 //   W3      K-split   CTA q: input columns [32q, 32q+32)            -> partial [NT][128]  -> cluster all-reduce
 //   W_in    4 mats    CTA q: hidden block q (columns [128q, 128q+128))                    -> stays local ...
 //   W_out   K-split   CTA q: rows [128q, 128q+128) = exactly the hidden block it produced -> partial -> all-reduce
@@ -224,7 +224,7 @@ __device__ __forceinline__ void group_layernorm(float (&v)[NJ], const float* __r
 // the result does not depend on timing.  LayerNorms are computed redundantly by the four CTAs.
 // Inside a CTA, thread (kq = tid/128, n = tid%128) takes rows [8kq, 8kq+8) of the 32-row chunk and column n.
 // ---------------------------------------------------------------------------
-constexpr int NC_RING = 6;
+constexpr int NC_SLOTS = 9;     // resident weight chunks per CTA of the cluster form
 constexpr int NC_THREADS = 512;
 
 // One CTA of the cluster plays one 128-thread group of node_update_step_kernel: the same per-(residue, column) FMA
@@ -238,49 +238,44 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NC_THREADS, 1) node_
     cg::cluster_group cluster = cg::this_cluster();
     const int q = (int)cluster.block_rank();
     extern __shared__ __align__(16) float smem[];
-    float* ring = smem;                              // [NC_RING][4096]
-    float* x = ring + NC_RING * WCHUNK_FLOATS;       // [NT][128]
-    float* hid = x + NT * HID;                       // [NT][128]  this CTA's block of the FFN hidden layer
-    float* xr = hid + NT * HID;                      // [NT][128]  this CTA's partial, read by the other three
-    float* red = xr + NT * HID;                      // [16][NJ]
+    float* ring = smem;                              // [NC_SLOTS][4096]: W3 | W_in x4 | W_out x4; projections reuse 1..4
+    float* x = ring + NC_SLOTS * WCHUNK_FLOATS;      // [NT][XP]   (padded rows, see tile_fma)
+    float* hid = x + NT * XP;                        // [NT][XP]   this CTA's block of the FFN hidden layer
+    float* xr0 = hid + NT * XP;                      // [NT][128]  this CTA's partials, read by the other three CTAs
+    float* xr1 = xr0 + NT * HID;                     //            (one buffer per all-reduce: no second cluster barrier)
+    float* red = xr1 + NT * HID;                     // [16][NJ]
     float* cnt_s = red + 16 * NJ;                    // [NT]
     const int g = threadIdx.x >> 7, n = threadIdx.x & 127;
+    // (Measured alternatives for the GEMM phases, both slower than one column x NJ residues per thread on all 16
+    // warps: 4 residues x 32 columns per warp with 1 x 4 thread tiles, +30 %; four warps holding all NT residues,
+    // +120 %.  At a dozen residues per CTA the phases are bound by per-warp latency, so more warps win.)
     const int node0 = (blockIdx.x >> 2) * NT;
     const float* wb = a.weights;
+#define NU_STAMP(i_) do { if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[i_] = clock64(); } while (0)
+    NU_STAMP(0);
 
-    const int nmine = 9 + ((a.nproj > 0 && q < a.nproj) ? 4 : 0);
-    auto chunk_src = [&](int k) -> const float* {   // step-major layout, chunk q of each step
-        if (k >= nmine) return nullptr;
-        return wb + a.w.stream + (size_t)(4 * k + q) * WCHUNK_FLOATS;
-    };
-    int issued = 0, got = 0;
-    auto issue = [&]() {
-        const float* src = chunk_src(issued);
-        if (src) {
-            float* dst = ring + (issued % NC_RING) * WCHUNK_FLOATS;
+    // This CTA's quarter of the weight stream (chunk q of every step) stays resident: nine chunks are requested up
+    // front -- before pdl_wait(), they are constants -- as nine cp.async groups, so the steps of a phase run without
+    // barriers or waits between them.  The four projection chunks take slots 1..4 once the FFN input layer is done.
+    const bool has_proj = a.nproj > 0 && q < a.nproj;
+    auto issue = [&](int k, int slot) {                // chunk k of this CTA -> slot; always one commit group
+        const float* src = wb + a.w.stream + (size_t)(4 * k + q) * WCHUNK_FLOATS;
+        float* dst = ring + slot * WCHUNK_FLOATS;
 #pragma unroll
-            for (int i = 0; i < WCHUNK_FLOATS / 4 / NC_THREADS; ++i) {
-                const int e = (threadIdx.x + i * NC_THREADS) * 4;
-                cp_async16(dst + e, src + e);
-            }
+        for (int i = 0; i < WCHUNK_FLOATS / 4 / NC_THREADS; ++i) {
+            const int e = (threadIdx.x + i * NC_THREADS) * 4;
+            cp_async16(dst + e, src + e);
         }
         cp_async_commit();
-        ++issued;
     };
     pdl_trigger();
 #pragma unroll
-    for (int k = 0; k < NC_RING - 1; ++k) issue();
-    pdl_wait();                                      // weights are constants; everything below reads earlier kernels' output
-    auto next_chunk = [&]() -> const float* {       // block-wide; also publishes earlier shared-memory writes
-        cp_async_wait<NC_RING - 2>();
-        __syncthreads();
-        issue();
-        const float* p = ring + (got % NC_RING) * WCHUNK_FLOATS;
-        ++got;
-        return p;
-    };
+    for (int k = 0; k < NC_SLOTS; ++k) issue(k, k);
+    NU_STAMP(1);
+    pdl_wait();                                      // everything below reads earlier kernels' output
+    NU_STAMP(2);
     // sum of the four CTAs' partials, in rank order (this thread: residues g + 4j, column n)
-    auto cluster_allreduce = [&](float (&v)[NJ]) {
+    auto cluster_allreduce = [&](float (&v)[NJ], float* xr) {
 #pragma unroll
         for (int j = 0; j < NJ; ++j) xr[(g + 4 * j) * HID + n] = v[j];
         cluster.sync();
@@ -293,8 +288,14 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NC_THREADS, 1) node_
             const int o = (g + 4 * j) * HID + n;
             v[j] = (r0[o] + r1[o]) + (r2[o] + r3[o]);
         }
-        cluster.sync();                              // xr may be rewritten
     };
+    // h_V rows of this thread's residues: requested now, used after the first all-reduce
+    float hv[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const int node = node0 + g + 4 * j;
+        hv[j] = node < a.N ? a.hV[(size_t)node * HID + n] : 0.f;
+    }
 
     if (a.Spart) {
         // neighbour sum = the three 16-row partials of the residue, added in order; weight count from E_idx
@@ -305,7 +306,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NC_THREADS, 1) node_
                 const float* sp = a.Spart + (size_t)node * 3 * HID + c;
                 s = (sp[0] + sp[HID]) + sp[2 * HID];
             }
-            x[i] = s;
+            x[(i / HID) * XP + c] = s;
         }
         for (int t = threadIdx.x >> 5; t < NT; t += NC_THREADS / 32) {   // one warp per residue
             const int lane = threadIdx.x & 31, node = node0 + t;
@@ -324,65 +325,83 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NC_THREADS, 1) node_
     } else {
         for (int i = threadIdx.x; i < NT * HID; i += NC_THREADS) {
             int node = node0 + i / HID;
-            x[i] = node < a.N ? a.Ssum[(size_t)node0 * HID + i] : 0.f;
+            x[(i / HID) * XP + i % HID] = node < a.N ? a.Ssum[(size_t)node0 * HID + i] : 0.f;
         }
         if (threadIdx.x < NT) cnt_s[threadIdx.x] = (node0 + threadIdx.x < a.N) ? a.cnt[node0 + threadIdx.x] : 0.f;
     }
 
     float acc[NJ], h[NJ];
+    NU_STAMP(3);
     // ---- W3 (this CTA: input columns 32q..)
 #pragma unroll
     for (int j = 0; j < NJ; ++j) acc[j] = 0.f;
-    step_fma<NJ>(acc, next_chunk(), x + g * HID + 32 * q, 4 * HID, n);
-    cluster_allreduce(acc);
+    cp_async_wait<NC_SLOTS - 1>();                   // chunk 0
+    __syncthreads();                                 // ... of every thread; also publishes x / cnt_s
+    step_fma<NJ>(acc, ring, x + g * XP + 32 * q, 4 * XP, n);
+    NU_STAMP(4);
+    cluster_allreduce(acc, xr0);
+    NU_STAMP(5);
     {
         const float b3 = __ldg(wb + a.w.b3 + n);
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            const int node = node0 + g + 4 * j;
-            const float hv = node < a.N ? a.hV[(size_t)node * HID + n] : 0.f;
-            h[j] = hv + fmaf(cnt_s[g + 4 * j], b3, acc[j]) / MSG_SCALE;
-        }
+        for (int j = 0; j < NJ; ++j) h[j] = hv[j] + fmaf(cnt_s[g + 4 * j], b3, acc[j]) / MSG_SCALE;
     }
     group_layernorm<NJ>(h, wb + a.w.n1.g, wb + a.w.n1.b, red);        // ends with a barrier: x is free
+    NU_STAMP(6);
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) x[(g + 4 * j) * HID + n] = h[j];
+    for (int j = 0; j < NJ; ++j) x[(g + 4 * j) * XP + n] = h[j];
     // ---- FFN 128 -> 512: this CTA's hidden block q
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) acc[j] = 0.f;
-    for (int s = 0; s < 4; ++s) step_fma<NJ>(acc, next_chunk(), x + g * HID + 32 * s, 4 * HID, n);
+    cp_async_wait<NC_SLOTS - 5>();                   // chunks 1..4
+    __syncthreads();                                 // + x
     {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc[j] = 0.f;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) step_fma<NJ>(acc, ring + (1 + s) * WCHUNK_FLOATS, x + g * XP + 32 * s, 4 * XP, n);
         const float bi = __ldg(wb + a.w.bin + q * HID + n);
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) hid[(g + 4 * j) * HID + n] = gelu_erf(acc[j] + bi);
+        for (int j = 0; j < NJ; ++j) hid[(g + 4 * j) * XP + n] = gelu_erf(acc[j] + bi);
     }
+    NU_STAMP(7);
     // ---- FFN 512 -> 128: rows 128q.. = the block above
+    cp_async_wait<0>();                              // chunks 5..8
+    __syncthreads();                                 // + hid; slots 1..4 are free
+    if (has_proj)
+#pragma unroll
+        for (int s = 0; s < 4; ++s) issue(9 + s, 1 + s);
 #pragma unroll
     for (int j = 0; j < NJ; ++j) acc[j] = 0.f;
-    for (int s = 0; s < 4; ++s) step_fma<NJ>(acc, next_chunk(), hid + g * HID + 32 * s, 4 * HID, n);
-    cluster_allreduce(acc);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) step_fma<NJ>(acc, ring + (5 + s) * WCHUNK_FLOATS, hid + g * XP + 32 * s, 4 * XP, n);
+    NU_STAMP(8);
+    cluster_allreduce(acc, xr1);
+    NU_STAMP(9);
     {
         const float bo = __ldg(wb + a.w.bout + n);
 #pragma unroll
         for (int j = 0; j < NJ; ++j) h[j] += acc[j] + bo;
     }
     group_layernorm<NJ>(h, wb + a.w.n2.g, wb + a.w.n2.b, red);
+    NU_STAMP(10);
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
         const int t = g + 4 * j, node = node0 + t;
         const float m = node < a.N ? a.maskf[node] : 0.f;
         h[j] *= m;
-        x[t * HID + n] = h[j];
+        x[t * XP + n] = h[j];
         if (node < a.N && q == 0) {
             a.hV[(size_t)node * HID + n] = h[j];
             if (a.hV_copy) a.hV_copy[(size_t)node * HID + n] = h[j];
         }
     }
     // ---- projections: CTA q computes projection q
-    if (a.nproj > 0 && q < a.nproj) {
+    if (has_proj) {
+        cp_async_wait<0>();
+        __syncthreads();                             // projection chunks + x
 #pragma unroll
         for (int j = 0; j < NJ; ++j) acc[j] = 0.f;
-        for (int s = 0; s < 4; ++s) step_fma<NJ>(acc, next_chunk(), x + g * HID + 32 * s, 4 * HID, n);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) step_fma<NJ>(acc, ring + (1 + s) * WCHUNK_FLOATS, x + g * XP + 32 * s, 4 * XP, n);
         const ProjSpec ps = a.proj[q];
         const float b = ps.bias >= 0 ? __ldg(wb + ps.bias + n) : 0.f;
 #pragma unroll
@@ -395,8 +414,10 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NC_THREADS, 1) node_
             }
         }
     }
+    NU_STAMP(11);
     cp_async_wait<0>();
     cluster.sync();      // no CTA may exit while another can still read its shared memory
+    NU_STAMP(12);
 }
 
 // ---------------------------------------------------------------------------
@@ -576,7 +597,7 @@ __global__ void __launch_bounds__(NK_THREADS, 1) head_kernel(HeadArgs a) {
 }
 
 template <int NT> static size_t smem_node_update() {
-    return sizeof(float) * (NC_RING * WCHUNK_FLOATS + 3 * NT * HID + 16 * (NT / 4) + NT);
+    return sizeof(float) * (NC_SLOTS * WCHUNK_FLOATS + 2 * NT * XP + 2 * NT * HID + 16 * (NT / 4) + NT);
 }
 template <int NT> static size_t smem_node_update_step() {
     return sizeof(float) * (2 * STEP_FLOATS + NT * XP + NT * HIDP + 16 * (NT / 4) + NT);

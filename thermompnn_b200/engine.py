@@ -166,6 +166,12 @@ class Engine:
         self._check(self._lib.tmpnn_fetch(self._ctx, b"tc_trace", a.ctypes.data, a.nbytes))
         return a
 
+    def fetch_node_trace(self) -> np.ndarray:
+        """TMPNN_TC_TRACE=1 only: clock64 stamps of the node_update cluster kernel (encoder layer 1, cluster 0)."""
+        a = np.zeros(64, dtype=np.int64)
+        self._check(self._lib.tmpnn_fetch(self._ctx, b"node_trace", a.ctypes.data, a.nbytes))
+        return a
+
     def set_debug_stop(self, stage: int):
         self._check(self._lib.tmpnn_set_debug_stop(self._ctx, stage))
 
