@@ -39,8 +39,7 @@ ALGO = {  # name: (flop_per_edge, flop_per_node, bytes_per_edge, bytes_per_node)
     "edge_upd": (2 * (384 + 128 + 128) * 128, 0, 1024 + 4, 512),
     "node_update": (0, 2 * 2 * 128 * 512, 0, 1024 + 4 * 512),
     "head": (0, 349504, 0, 3 * 512 + 84),
-    "knn": (0, 0, 8, 64),
-    "prep_nodes": (0, 0, 0, 112),
+    "knn": (0, 0, 8, 64 + 112),
 }
 
 

@@ -72,7 +72,6 @@ struct tmpnn_ctx {
     cudaEvent_t stage_ev = nullptr;   // completion of the last H2D out of h_stage
     bool stage_busy = false;
     // per-node
-    DevBuf<int> pstart, pend;
     DevBuf<float> atoms, maskf, hV, dec_prev, dec_last, Ssum, cnt, P, Q, P2, Q2, table, Spart;
     // per-edge
     DevBuf<int> E_idx;
@@ -499,7 +498,6 @@ void tmpnn_destroy(tmpnn_ctx* ctx) {
     if (ctx->d_weights) cudaFree(ctx->d_weights);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     ctx->d_in.release();
-    ctx->pstart.release(); ctx->pend.release();
     ctx->atoms.release(); ctx->maskf.release(); ctx->hV.release(); ctx->dec_prev.release(); ctx->dec_last.release();
     ctx->Ssum.release(); ctx->cnt.release(); ctx->P.release(); ctx->Q.release(); ctx->P2.release(); ctx->Q2.release();
     ctx->Spart.release();
@@ -601,7 +599,6 @@ int tmpnn_run_batch(tmpnn_ctx* ctx, int32_t B, const int32_t* offsets, const flo
 
     // ---- buffers --------------------------------------------------------------
     const size_t n = (size_t)N, ne = n * KNB;
-    CU(ctx->pstart.reserve(n)); CU(ctx->pend.reserve(n));
     CU(ctx->atoms.reserve(n * 16)); CU(ctx->maskf.reserve(n));
     CU(ctx->hV.reserve(n * HID)); CU(ctx->dec_prev.reserve(n * HID)); CU(ctx->dec_last.reserve(n * HID));
     CU(ctx->Ssum.reserve(n * HID)); CU(ctx->cnt.reserve(n)); CU(ctx->Spart.reserve(n * 3 * HID));
@@ -626,10 +623,8 @@ int tmpnn_run_batch(tmpnn_ctx* ctx, int32_t B, const int32_t* offsets, const flo
     // (h_V starts at zero, protein_mpnn_utils.py:1225; cleared up front so that no memset sits between two kernels
     // of the programmatic-dependent-launch chain)
     CU(cudaMemsetAsync(ctx->hV.p, 0, n * HID * sizeof(float), st));
-    { LaunchScope ls(ctx, st, "prep_nodes");
-      launch_prep_nodes(d_off, B, d_X, d_m, N, ctx->pstart.p, ctx->pend.p, ctx->atoms.p, ctx->maskf.p, st); }
     { LaunchScope ls(ctx, st, "knn");
-      launch_knn(ctx->atoms.p, ctx->maskf.p, ctx->pstart.p, ctx->pend.p, N, lmax, ctx->E_idx.p, ctx->D_nb.p, st); }
+      launch_knn(d_off, B, d_X, d_m, N, lmax, ctx->atoms.p, ctx->maskf.p, ctx->E_idx.p, ctx->D_nb.p, st); }
     if (!stage_done(1)) {
         if (ctx->tc_mask & 1) {
             LaunchScope ls(ctx, st, "tc_edge_feat");

@@ -2,7 +2,7 @@
 //
 // Pipeline for a ragged batch of proteins (N residues in total, 48 neighbour slots each):
 //
-//   prep_nodes      backbone atoms + virtual Cb, residue -> protein range      protein_mpnn_utils.py:1131-1138
+//   knn (first part) backbone atoms + virtual Cb, residue -> protein range      protein_mpnn_utils.py:1131-1138
 //   knn             48 nearest CA neighbours per residue, ascending            :1101-1109
 //   edge_feat       25x16 RBF + positional -> 416->128 -> LN -> W_e  => h_E    :1111-1125, 1142-1179, 1229
 //   msg<ENC>        per edge W1b.h_E + P_i + Q_j -> GELU -> W2 -> GELU, masked sum over neighbours  :819-825
@@ -30,50 +30,15 @@ __constant__ int8_t c_pair_a[NPAIR] = {1, 0, 2, 3, 4, 1, 1, 1, 1, 0, 0, 0, 4, 4,
 __constant__ int8_t c_pair_b[NPAIR] = {1, 0, 2, 3, 4, 0, 2, 3, 4, 2, 3, 4, 2, 3, 2, 1, 1, 1, 1, 0, 0, 0, 4, 4, 3};
 
 // ---------------------------------------------------------------------------
-// prep_nodes
-// ---------------------------------------------------------------------------
-__global__ void prep_nodes_kernel(const int* __restrict__ offsets, int B, const float* __restrict__ X,
-                                  const uint8_t* __restrict__ mask_u8, int N, int* __restrict__ pstart,
-                                  int* __restrict__ pend, float* __restrict__ atoms, float* __restrict__ maskf) {
-    pdl_trigger();
-    pdl_wait();
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    int lo = 0, hi = B;  // find b with offsets[b] <= i < offsets[b+1]
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (offsets[mid] <= i) lo = mid; else hi = mid;
-    }
-    pstart[i] = offsets[lo];
-    pend[i] = offsets[lo + 1];
-    maskf[i] = mask_u8[i] ? 1.0f : 0.0f;
-    const float* x = X + (size_t)i * 12;
-    float n[3] = {x[0], x[1], x[2]}, ca[3] = {x[3], x[4], x[5]}, c[3] = {x[6], x[7], x[8]};
-    float b[3], cc[3], a[3];
-    for (int d = 0; d < 3; ++d) { b[d] = __fsub_rn(ca[d], n[d]); cc[d] = __fsub_rn(c[d], ca[d]); }
-    a[0] = __fsub_rn(__fmul_rn(b[1], cc[2]), __fmul_rn(b[2], cc[1]));
-    a[1] = __fsub_rn(__fmul_rn(b[2], cc[0]), __fmul_rn(b[0], cc[2]));
-    a[2] = __fsub_rn(__fmul_rn(b[0], cc[1]), __fmul_rn(b[1], cc[0]));
-    float* o = atoms + (size_t)i * 16;
-    for (int d = 0; d < 12; ++d) o[d] = x[d];
-    for (int d = 0; d < 3; ++d) {
-        float t = __fadd_rn(__fmul_rn(-0.58273431f, a[d]), __fmul_rn(0.56802827f, b[d]));
-        t = __fsub_rn(t, __fmul_rn(0.54067466f, cc[d]));
-        o[12 + d] = __fadd_rn(t, ca[d]);
-    }
-    o[15] = 0.f;
-}
-
-// ---------------------------------------------------------------------------
-// knn: one warp per residue; the row of masked distances lives in shared memory.  The K-th smallest distance is
+// knn (+ node preparation): one warp per residue; the row of masked distances lives in shared memory.  The K-th smallest distance is
 // found by a bitwise (radix) search on the float pattern (all values are >= 0, so uint order == float order): 31 rounds
 // of "count keys below the trial value" with a warp-wide integer reduction.  The K winners (ties at the threshold: lowest
 // index first) are compacted with ballots and ordered by (distance, index) with a 48-element rank sort, which gives
 // exactly torch.topk's ascending output with self first.
 // ---------------------------------------------------------------------------
-__global__ void knn_kernel(const float* __restrict__ atoms, const float* __restrict__ maskf,
-                           const int* __restrict__ pstart, const int* __restrict__ pend, int N, int lmax,
-                           int* __restrict__ E_idx, float* __restrict__ D_nb) {
+__global__ void knn_kernel(const int* __restrict__ offsets, int B, const float* __restrict__ X,
+                           const uint8_t* __restrict__ mask_u8, int N, int lmax, float* __restrict__ atoms,
+                           float* __restrict__ maskf, int* __restrict__ E_idx, float* __restrict__ D_nb) {
     pdl_trigger();
     pdl_wait();
     extern __shared__ float s_row[];
@@ -84,22 +49,55 @@ __global__ void knn_kernel(const float* __restrict__ atoms, const float* __restr
     float* d = s_row + (size_t)w * (lmax + 2 * KNB);
     float* selv = d + lmax;                               // [48] selected distances
     int* seli = reinterpret_cast<int*>(selv + KNB);       // [48] selected local indices
-    const int s = pstart[i], L = pend[i] - s;
-    const float xi = atoms[(size_t)i * 16 + 3], yi = atoms[(size_t)i * 16 + 4], zi = atoms[(size_t)i * 16 + 5];
-    const float mi = maskf[i];
+    // ---- this residue's protein: offsets[b] <= i < offsets[b+1]  (all lanes probe the sorted offsets at once)
+    int nle = 0;
+    for (int b = lane; b <= B; b += 32) nle += (offsets[b] <= i) ? 1 : 0;
+    nle = __reduce_add_sync(0xffffffffu, nle);
+    const int s = offsets[nle - 1], L = offsets[nle] - s;
+    // ---- node preparation (what the other kernels read): N, CA, C, O and the virtual C-beta (protein_mpnn_utils.py:1133-1136);
+    // lane d < 12 holds coordinate d of the residue
+    const float xd = X[(size_t)i * 12 + (lane < 12 ? lane : 0)];
+    float x9[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) x9[q] = __shfl_sync(0xffffffffu, xd, q);
+    const float xi = x9[3], yi = x9[4], zi = x9[5];
+    const float mi = mask_u8[i] ? 1.0f : 0.0f;
+    if (lane < 16) {
+        float v = xd;
+        if (lane >= 12) {
+            float b[3], cc[3], a[3];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) { b[q] = __fsub_rn(x9[3 + q], x9[q]); cc[q] = __fsub_rn(x9[6 + q], x9[3 + q]); }
+            a[0] = __fsub_rn(__fmul_rn(b[1], cc[2]), __fmul_rn(b[2], cc[1]));
+            a[1] = __fsub_rn(__fmul_rn(b[2], cc[0]), __fmul_rn(b[0], cc[2]));
+            a[2] = __fsub_rn(__fmul_rn(b[0], cc[1]), __fmul_rn(b[1], cc[0]));
+            const int q = lane - 12;
+            v = 0.f;
+            if (q < 3) {
+                const float aq = q == 0 ? a[0] : (q == 1 ? a[1] : a[2]), bq = q == 0 ? b[0] : (q == 1 ? b[1] : b[2]);
+                const float cq = q == 0 ? cc[0] : (q == 1 ? cc[1] : cc[2]), caq = q == 0 ? x9[3] : (q == 1 ? x9[4] : x9[5]);
+                float t = __fadd_rn(__fmul_rn(-0.58273431f, aq), __fmul_rn(0.56802827f, bq));
+                t = __fsub_rn(t, __fmul_rn(0.54067466f, cq));
+                v = __fadd_rn(t, caq);
+            }
+        }
+        atoms[(size_t)i * 16 + lane] = v;
+        if (lane == 0) maskf[i] = mi;
+    }
+    // ---- masked CA-CA distances of the row (inputs read directly: other warps are still writing atoms / maskf)
     float dmax = 0.f;
     for (int j = lane; j < L; j += 32) {
-        const float* aj = atoms + (size_t)(s + j) * 16;
-        float dx = __fsub_rn(aj[3], xi), dy = __fsub_rn(aj[4], yi), dz = __fsub_rn(aj[5], zi);
+        const float* aj = X + (size_t)(s + j) * 12 + 3;
+        float dx = __fsub_rn(aj[0], xi), dy = __fsub_rn(aj[1], yi), dz = __fsub_rn(aj[2], zi);
         float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-        float D = __fmul_rn(mi * maskf[s + j], __fsqrt_rn(__fadd_rn(d2, 1e-6f)));
+        float D = __fmul_rn(mi * (mask_u8[s + j] ? 1.0f : 0.0f), __fsqrt_rn(__fadd_rn(d2, 1e-6f)));
         d[j] = D;
         dmax = fmaxf(dmax, D);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
     for (int j = lane; j < L; j += 32) {
-        float m2 = mi * maskf[s + j];
+        float m2 = mi * (mask_u8[s + j] ? 1.0f : 0.0f);
         d[j] = __fadd_rn(d[j], __fmul_rn(1.0f - m2, dmax));      // masked pairs pushed to the row maximum (:1105-1106)
     }
     __syncwarp();
@@ -482,20 +480,15 @@ cudaError_t kernels_init() {
     return cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
 
-void launch_prep_nodes(const int* offsets, int B, const float* X, const uint8_t* mask, int N, int* pstart, int* pend,
-                       float* atoms, float* maskf, cudaStream_t st) {
-    launch_pdl(prep_nodes_kernel, dim3((N + 127) / 128), dim3(128), 0, st, offsets, B, X, mask, N, pstart, pend, atoms, maskf);
-}
-
 int knn_max_len() { return 200 * 1024 / 4 - 2 * KNB; }
 
-void launch_knn(const float* atoms, const float* maskf, const int* pstart, const int* pend, int N, int lmax,
+void launch_knn(const int* offsets, int B, const float* X, const uint8_t* mask, int N, int lmax, float* atoms, float* maskf,
                 int* E_idx, float* D_nb, cudaStream_t st) {
     int warps = 8;
     const size_t per_warp = (size_t)(lmax + 2 * KNB) * 4;
     while (warps > 1 && (size_t)warps * per_warp > 200 * 1024) warps >>= 1;
     size_t smem = (size_t)warps * per_warp;
-    launch_pdl(knn_kernel, dim3((N + warps - 1) / warps), dim3(warps * 32), smem, st, atoms, maskf, pstart, pend, N, lmax, E_idx, D_nb);
+    launch_pdl(knn_kernel, dim3((N + warps - 1) / warps), dim3(warps * 32), smem, st, offsets, B, X, mask, N, lmax, atoms, maskf, E_idx, D_nb);
 }
 
 #define TMPNN_DISPATCH_NPT(npt, CALL)  \

@@ -47,9 +47,8 @@ cudaError_t tc_kernels_init();
 cudaError_t tc_take_error();   // sticky host-side error of the tensor-core launchers (tensor-map encoding), cleared on read
 int knn_max_len();
 
-void launch_prep_nodes(const int* offsets, int B, const float* X, const uint8_t* mask, int N, int* pstart, int* pend,
-                       float* atoms, float* maskf, cudaStream_t st);
-void launch_knn(const float* atoms, const float* maskf, const int* pstart, const int* pend, int N, int lmax,
+// first kernel of a call: per-residue atoms (N, CA, C, O, virtual C-beta) and float mask, then the k-NN graph
+void launch_knn(const int* offsets, int B, const float* X, const uint8_t* mask, int N, int lmax, float* atoms, float* maskf,
                 int* E_idx, float* D_nb, cudaStream_t st);
 void launch_edge_feat(int npt, const float* atoms, const int* E_idx, const float* D_nb, const int* ridx,
                       const int* cenc, const float* pos_table, const float* rbf_mu, const float* wstream,
