@@ -36,6 +36,9 @@ __constant__ int8_t c_pair_b[NPAIR] = {1, 0, 2, 3, 4, 0, 2, 3, 4, 2, 3, 4, 2, 3,
 // index first) are compacted with ballots and ordered by (distance, index) with a 48-element rank sort, which gives
 // exactly torch.topk's ascending output with self first.
 // ---------------------------------------------------------------------------
+// NPL > 0: proteins of at most 32 NPL residues -- the row of distances lives in registers (NPL keys per lane), so the 31
+// selection rounds touch no memory and all the row's loads are in flight at once.  NPL = 0: any length, row in smem.
+template <int NPL>
 __global__ void knn_kernel(const int* __restrict__ offsets, int B, const float* __restrict__ X,
                            const uint8_t* __restrict__ mask_u8, int N, int lmax, float* __restrict__ atoms,
                            float* __restrict__ maskf, int* __restrict__ E_idx, float* __restrict__ D_nb) {
@@ -46,8 +49,9 @@ __global__ void knn_kernel(const int* __restrict__ offsets, int B, const float* 
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = blockIdx.x * warps + w;
     if (i >= N) return;  // no block-level barriers below
-    float* d = s_row + (size_t)w * (lmax + 2 * KNB);
-    float* selv = d + lmax;                               // [48] selected distances
+    const int rowlen = NPL > 0 ? 0 : lmax;
+    float* d = s_row + (size_t)w * (rowlen + 2 * KNB);
+    float* selv = d + rowlen;                             // [48] selected distances
     int* seli = reinterpret_cast<int*>(selv + KNB);       // [48] selected local indices
     // ---- this residue's protein: offsets[b] <= i < offsets[b+1]  (all lanes probe the sorted offsets at once)
     int nle = 0;
@@ -85,42 +89,18 @@ __global__ void knn_kernel(const int* __restrict__ offsets, int B, const float* 
         if (lane == 0) maskf[i] = mi;
     }
     // ---- masked CA-CA distances of the row (inputs read directly: other warps are still writing atoms / maskf)
-    float dmax = 0.f;
-    for (int j = lane; j < L; j += 32) {
+    auto dist = [&](int j, float& m2) -> float {
         const float* aj = X + (size_t)(s + j) * 12 + 3;
         float dx = __fsub_rn(aj[0], xi), dy = __fsub_rn(aj[1], yi), dz = __fsub_rn(aj[2], zi);
         float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-        float D = __fmul_rn(mi * (mask_u8[s + j] ? 1.0f : 0.0f), __fsqrt_rn(__fadd_rn(d2, 1e-6f)));
-        d[j] = D;
-        dmax = fmaxf(dmax, D);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
-    for (int j = lane; j < L; j += 32) {
-        float m2 = mi * (mask_u8[s + j] ? 1.0f : 0.0f);
-        d[j] = __fadd_rn(d[j], __fmul_rn(1.0f - m2, dmax));      // masked pairs pushed to the row maximum (:1105-1106)
-    }
-    __syncwarp();
+        m2 = mi * (mask_u8[s + j] ? 1.0f : 0.0f);
+        return __fmul_rn(m2, __fsqrt_rn(__fadd_rn(d2, 1e-6f)));
+    };
     const int K = L < KNB ? L : KNB;
-    // ---- threshold = K-th smallest key
-    uint32_t T = 0;
-    for (int bit = 30; bit >= 0; --bit) {
-        const uint32_t trial = T | (1u << bit);
-        int cnt = 0;
-        for (int j = lane; j < L; j += 32) cnt += (__float_as_uint(d[j]) < trial) ? 1 : 0;
-        cnt = __reduce_add_sync(0xffffffffu, cnt);
-        if (cnt < K) T = trial;
-    }
-    int n_less = 0;
-    for (int j = lane; j < L; j += 32) n_less += (__float_as_uint(d[j]) < T) ? 1 : 0;
-    n_less = __reduce_add_sync(0xffffffffu, n_less);
-    const int need_eq = K - n_less;                       // how many keys equal to T to take, in index order
-    // ---- compaction
-    int out_pos = 0, eq_seen = 0;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    for (int base = 0; base < L; base += 32) {
-        const int j = base + lane;
-        const uint32_t key = j < L ? __float_as_uint(d[j]) : 0xffffffffu;
+    int out_pos = 0, eq_seen = 0;
+    // one 32-wide slice of the row: take keys below T, and the first need_eq keys equal to T in index order
+    auto compact = [&](uint32_t key, int j, uint32_t T, int need_eq) {
         const bool is_lt = key < T, is_eq = key == T;
         const uint32_t b_eq = __ballot_sync(0xffffffffu, is_eq);
         const bool take = is_lt || (is_eq && (eq_seen + __popc(b_eq & lt_mask)) < need_eq);
@@ -132,6 +112,74 @@ __global__ void knn_kernel(const int* __restrict__ offsets, int B, const float* 
         }
         out_pos += __popc(b_take);
         eq_seen += __popc(b_eq);
+    };
+    if (NPL > 0) {
+        uint32_t key[NPL > 0 ? NPL : 1];
+        float m2r[NPL > 0 ? NPL : 1];
+        float dmax = 0.f;
+#pragma unroll
+        for (int q = 0; q < NPL; ++q) {
+            const int j = lane + 32 * q;
+            float D = 0.f;
+            m2r[q] = 1.0f;
+            if (j < L) { D = dist(j, m2r[q]); dmax = fmaxf(dmax, D); }
+            key[q] = __float_as_uint(D);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+#pragma unroll
+        for (int q = 0; q < NPL; ++q) {      // masked pairs pushed to the row maximum (:1105-1106); padding never selected
+            const float D = __fadd_rn(__uint_as_float(key[q]), __fmul_rn(1.0f - m2r[q], dmax));
+            key[q] = (lane + 32 * q < L) ? __float_as_uint(D) : 0xffffffffu;
+        }
+        uint32_t T = 0;                       // threshold = K-th smallest key (bitwise search, all keys >= 0)
+        for (int bit = 30; bit >= 0; --bit) {
+            const uint32_t trial = T | (1u << bit);
+            int cnt = 0;
+#pragma unroll
+            for (int q = 0; q < NPL; ++q) cnt += (key[q] < trial) ? 1 : 0;
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            if (cnt < K) T = trial;
+        }
+        int n_less = 0;
+#pragma unroll
+        for (int q = 0; q < NPL; ++q) n_less += (key[q] < T) ? 1 : 0;
+        n_less = __reduce_add_sync(0xffffffffu, n_less);
+        const int need_eq = K - n_less;
+#pragma unroll
+        for (int q = 0; q < NPL; ++q)
+            if (32 * q < L) compact(key[q], lane + 32 * q, T, need_eq);
+    } else {
+        float dmax = 0.f;
+        for (int j = lane; j < L; j += 32) {
+            float m2;
+            const float D = dist(j, m2);
+            d[j] = D;
+            dmax = fmaxf(dmax, D);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+        for (int j = lane; j < L; j += 32) {
+            float m2 = mi * (mask_u8[s + j] ? 1.0f : 0.0f);
+            d[j] = __fadd_rn(d[j], __fmul_rn(1.0f - m2, dmax));      // masked pairs pushed to the row maximum (:1105-1106)
+        }
+        __syncwarp();
+        uint32_t T = 0;
+        for (int bit = 30; bit >= 0; --bit) {
+            const uint32_t trial = T | (1u << bit);
+            int cnt = 0;
+            for (int j = lane; j < L; j += 32) cnt += (__float_as_uint(d[j]) < trial) ? 1 : 0;
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            if (cnt < K) T = trial;
+        }
+        int n_less = 0;
+        for (int j = lane; j < L; j += 32) n_less += (__float_as_uint(d[j]) < T) ? 1 : 0;
+        n_less = __reduce_add_sync(0xffffffffu, n_less);
+        const int need_eq = K - n_less;                       // how many keys equal to T to take, in index order
+        for (int base = 0; base < L; base += 32) {
+            const int j = base + lane;
+            compact(j < L ? __float_as_uint(d[j]) : 0xffffffffu, j, T, need_eq);
+        }
     }
     __syncwarp();
     // ---- order by (distance, index): rank sort of K <= 48 entries
@@ -477,7 +525,7 @@ cudaError_t kernels_init() {
     if ((e = set_smem(edge_upd_kernel<NPT>, smem_edge_upd<NPT>())) != cudaSuccess) return e;
     TMPNN_INIT_NPT(1) TMPNN_INIT_NPT(2) TMPNN_INIT_NPT(3) TMPNN_INIT_NPT(4)
 #undef TMPNN_INIT_NPT
-    return cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    return cudaFuncSetAttribute(knn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
 
 int knn_max_len() { return 200 * 1024 / 4 - 2 * KNB; }
@@ -485,10 +533,15 @@ int knn_max_len() { return 200 * 1024 / 4 - 2 * KNB; }
 void launch_knn(const int* offsets, int B, const float* X, const uint8_t* mask, int N, int lmax, float* atoms, float* maskf,
                 int* E_idx, float* D_nb, cudaStream_t st) {
     int warps = 8;
-    const size_t per_warp = (size_t)(lmax + 2 * KNB) * 4;
+    const int rowlen = lmax <= 512 ? 0 : lmax;            // register-resident rows up to 512 residues
+    const size_t per_warp = (size_t)(rowlen + 2 * KNB) * 4;
     while (warps > 1 && (size_t)warps * per_warp > 200 * 1024) warps >>= 1;
-    size_t smem = (size_t)warps * per_warp;
-    launch_pdl(knn_kernel, dim3((N + warps - 1) / warps), dim3(warps * 32), smem, st, offsets, B, X, mask, N, lmax, atoms, maskf, E_idx, D_nb);
+    const size_t smem = (size_t)warps * per_warp;
+    const dim3 grid((N + warps - 1) / warps), block(warps * 32);
+    if (lmax <= 128) launch_pdl(knn_kernel<4>, grid, block, smem, st, offsets, B, X, mask, N, lmax, atoms, maskf, E_idx, D_nb);
+    else if (lmax <= 256) launch_pdl(knn_kernel<8>, grid, block, smem, st, offsets, B, X, mask, N, lmax, atoms, maskf, E_idx, D_nb);
+    else if (lmax <= 512) launch_pdl(knn_kernel<16>, grid, block, smem, st, offsets, B, X, mask, N, lmax, atoms, maskf, E_idx, D_nb);
+    else launch_pdl(knn_kernel<0>, grid, block, smem, st, offsets, B, X, mask, N, lmax, atoms, maskf, E_idx, D_nb);
 }
 
 #define TMPNN_DISPATCH_NPT(npt, CALL)  \
