@@ -716,7 +716,7 @@ int tmpnn_run_batch(tmpnn_ctx* ctx, int32_t B, const int32_t* offsets, const flo
         h.weights = W; h.stream = L.head; h.Ws = L.Ws; h.la_b = L.la_b; h.m1_b = L.m1_b; h.m2_b = L.m2_b;
         h.m3_b = L.m3_b; h.ddg = L.ddg;
         h.dec_last = ctx->dec_last.p; h.dec_prev = ctx->dec_prev.p; h.S = d_S; h.table = d_table; h.N = N;
-        { LaunchScope ls(ctx, st, "head"); launch_head(h, st); }
+        { LaunchScope ls(ctx, st, "head"); launch_head(h, ctx->sm_count, st); }
         if (!out_dev) CU(cudaMemcpyAsync(out_table, d_table, n * 21 * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
     CU(cudaGetLastError());

@@ -69,6 +69,6 @@ void launch_tc_msg(bool dec, const float* hE, const int* E_idx, const float* P, 
                    const float* maskf, const float* wimg, const float* b2, float* Spart, int N, int sms, cudaStream_t st,
                    long long* trace = nullptr);
 void launch_node_update(const NodeUpdArgs& a, int sms, cudaStream_t st);
-void launch_head(const HeadArgs& a, cudaStream_t st);
+void launch_head(const HeadArgs& a, int sms, cudaStream_t st);
 
 }  // namespace tmpnn

@@ -596,11 +596,132 @@ __global__ void __launch_bounds__(NK_THREADS, 1) head_kernel(HeadArgs a) {
     cp_async_wait<0>();
 }
 
+// ---------------------------------------------------------------------------
+// head, cluster form for SMALL batches (the step form streams all 0.9 MB of head weights through every block, which
+// at a few dozen blocks is one long exposed L2 -> SM stream).  As in node_update_kernel, CTA q of a 4-CTA cluster plays
+// group q of head_kernel: chunk q of each of the 14 steps, the same per-(residue, column) chains, partials exchanged
+// through distributed shared memory and added in rank order -- bit-identical to the step form.
+// Weight chunks: 0..8 (LightAttention) requested up front, before the dependency wait; 9..11 take slots 0..2 once
+// block 0 is done, 12..13 slots 3..4 once block 1 is done.
+// ---------------------------------------------------------------------------
+template <int NT>
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NC_THREADS, 1) head_cluster_kernel(HeadArgs a) {
+    constexpr int NJ = NT / 4;
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int q = (int)cluster.block_rank();
+    extern __shared__ __align__(16) float smem[];
+    float* ring = smem;                              // [NC_SLOTS][4096]
+    float* x = ring + NC_SLOTS * WCHUNK_FLOATS;      // [NT][384]; later z1 [NT][128]
+    float* y = x + NT * 3 * HID;                     // [NT][384]; later z2 [NT][128]
+    float* xr0 = y + NT * 3 * HID;                   // [NT][128] partials, one buffer per parity of the all-reduce
+    float* xr1 = xr0 + NT * HID;
+    const int g = threadIdx.x >> 7, n = threadIdx.x & 127;
+    const int node0 = (blockIdx.x >> 2) * NT;
+    const float* wb = a.weights;
+    auto issue = [&](int k, int slot) {              // chunk q of step k -> slot (no commit)
+        const float* src = wb + a.stream + (size_t)(4 * k + q) * WCHUNK_FLOATS;
+        float* dst = ring + slot * WCHUNK_FLOATS;
+#pragma unroll
+        for (int i = 0; i < WCHUNK_FLOATS / 4 / NC_THREADS; ++i) {
+            const int e = (threadIdx.x + i * NC_THREADS) * 4;
+            cp_async16(dst + e, src + e);
+        }
+    };
+    pdl_trigger();
+#pragma unroll
+    for (int k = 0; k < NC_SLOTS; ++k) { issue(k, k); cp_async_commit(); }
+    pdl_wait();
+    for (int i = threadIdx.x; i < NT * HID; i += NC_THREADS) {
+        int t = i / HID, c = i % HID, node = node0 + t;
+        bool ok = node < a.N;
+        x[t * 3 * HID + c] = ok ? a.dec_last[(size_t)node * HID + c] : 0.f;
+        x[t * 3 * HID + HID + c] = ok ? a.dec_prev[(size_t)node * HID + c] : 0.f;
+        x[t * 3 * HID + 2 * HID + c] = ok ? __ldg(wb + a.Ws + (size_t)a.S[node] * HID + c) : 0.f;
+    }
+    int ar = 0;
+    // K-split phase of `steps` steps on input rows xin (row pitch ldx): this CTA takes rows [(q steps + s) 32, +32)
+    auto phase = [&](float (&res)[NJ], int steps, int slot0, const float* xin, int ldx) {
+        float acc[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc[j] = 0.f;
+        for (int s = 0; s < steps; ++s)
+            step_fma<NJ>(acc, ring + (slot0 + s) * WCHUNK_FLOATS, xin + g * ldx + (q * steps + s) * WCHUNK_K, 4 * ldx, n);
+        float* xr = (ar++ & 1) ? xr1 : xr0;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) xr[(g + 4 * j) * HID + n] = acc[j];
+        cluster.sync();
+        const float* r0 = cluster.map_shared_rank(xr, 0);
+        const float* r1 = cluster.map_shared_rank(xr, 1);
+        const float* r2 = cluster.map_shared_rank(xr, 2);
+        const float* r3 = cluster.map_shared_rank(xr, 3);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int o = (g + 4 * j) * HID + n;
+            res[j] = (r0[o] + r1[o]) + (r2[o] + r3[o]);
+        }
+    };
+    float res[NJ];
+    // ---- LightAttention centre tap, three column blocks of 128 (K = 384)
+    cp_async_wait<6>(); __syncthreads();             // chunks 0..2 + x
+    phase(res, 3, 0, x, 3 * HID);
+    issue(9, 0); issue(10, 1); issue(11, 2); cp_async_commit();      // slots 0..2 are free (cluster barrier above)
+    {
+        const float b = __ldg(wb + a.la_b + n);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) y[(g + 4 * j) * 3 * HID + n] = fmaxf(res[j] + b, 0.f);
+    }
+    cp_async_wait<4>(); __syncthreads();             // chunks 3..5
+    phase(res, 3, 3, x, 3 * HID);
+    issue(12, 3); issue(13, 4); cp_async_commit();
+    {
+        const float b = __ldg(wb + a.la_b + HID + n);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) y[(g + 4 * j) * 3 * HID + HID + n] = fmaxf(res[j] + b, 0.f);
+    }
+    cp_async_wait<2>(); __syncthreads();             // chunks 6..8
+    phase(res, 3, 6, x, 3 * HID);
+    {
+        const float b = __ldg(wb + a.la_b + 2 * HID + n);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) y[(g + 4 * j) * 3 * HID + 2 * HID + n] = fmaxf(res[j] + b, 0.f);
+    }
+    // ---- both_out MLP
+    cp_async_wait<1>(); __syncthreads();             // chunks 9..11 + y
+    phase(res, 3, 0, y, 3 * HID);
+    {
+        const float b = n < 64 ? __ldg(wb + a.m1_b + n) : 0.f;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) x[(g + 4 * j) * HID + n] = fmaxf(res[j] + b, 0.f);   // z1 (columns >= 64 are 0)
+    }
+    cp_async_wait<0>(); __syncthreads();             // chunks 12, 13 + z1
+    phase(res, 1, 3, x, HID);
+    {
+        const float b = n < 32 ? __ldg(wb + a.m2_b + n) : 0.f;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) y[(g + 4 * j) * HID + n] = fmaxf(res[j] + b, 0.f);   // z2 (columns >= 32 are 0)
+    }
+    __syncthreads();
+    phase(res, 1, 4, y, HID);
+    if (q == 0 && n < 21) {
+        const float b = __ldg(wb + a.m3_b + n), sc = __ldg(wb + a.ddg), sh = __ldg(wb + a.ddg + 1);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            int node = node0 + g + 4 * j;
+            if (node < a.N) a.table[(size_t)node * 21 + n] = fmaf(res[j] + b, sc, sh);   // ddg_out: Linear(1,1)
+        }
+    }
+    cluster.sync();      // no CTA may exit while another can still read its shared memory
+}
+
 template <int NT> static size_t smem_node_update() {
     return sizeof(float) * (NC_SLOTS * WCHUNK_FLOATS + 2 * NT * XP + 2 * NT * HID + 16 * (NT / 4) + NT);
 }
 template <int NT> static size_t smem_node_update_step() {
     return sizeof(float) * (2 * STEP_FLOATS + NT * XP + NT * HIDP + 16 * (NT / 4) + NT);
+}
+template <int NT> static size_t smem_head_cluster() {
+    return sizeof(float) * (NC_SLOTS * WCHUNK_FLOATS + 2 * NT * 3 * HID + 2 * NT * HID);
 }
 template <int NT> static size_t smem_head() {
     return sizeof(float) * (2 * STEP_FLOATS + 2 * NT * 3 * HID + 4 * NT * HID);
@@ -614,6 +735,9 @@ cudaError_t node_kernels_init() {
     if ((e = cudaFuncSetAttribute(node_update_step_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_node_update_step<16>())) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(node_update_step_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_node_update_step<32>())) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(head_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_head<8>())) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(head_cluster_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_head_cluster<8>())) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(head_cluster_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_head_cluster<12>())) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(head_cluster_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_head_cluster<16>())) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
@@ -635,8 +759,17 @@ void launch_node_update(const NodeUpdArgs& a, int sms, cudaStream_t st) {
     }
 }
 
-void launch_head(const HeadArgs& a, cudaStream_t st) {
-    launch_pdl(head_kernel<8>, dim3((a.N + 7) / 8), dim3(NK_THREADS), smem_head<8>(), st, a);
+void launch_head(const HeadArgs& a, int sms, cudaStream_t st) {
+    const int N = a.N;   // same dispatch rule as launch_node_update; all forms bit-identical per residue
+    if (4 * ((N + 7) / 8) <= sms) {
+        launch_pdl(head_cluster_kernel<8>, dim3(4 * ((N + 7) / 8)), dim3(NC_THREADS), smem_head_cluster<8>(), st, a);
+    } else if (4 * ((N + 11) / 12) <= sms) {
+        launch_pdl(head_cluster_kernel<12>, dim3(4 * ((N + 11) / 12)), dim3(NC_THREADS), smem_head_cluster<12>(), st, a);
+    } else if (4 * ((N + 15) / 16) <= sms) {
+        launch_pdl(head_cluster_kernel<16>, dim3(4 * ((N + 15) / 16)), dim3(NC_THREADS), smem_head_cluster<16>(), st, a);
+    } else {
+        launch_pdl(head_kernel<8>, dim3((N + 7) / 8), dim3(NK_THREADS), smem_head<8>(), st, a);
+    }
 }
 
 }  // namespace tmpnn
