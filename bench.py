@@ -26,6 +26,19 @@ import time
 
 import numpy as np
 
+# stdout carries exactly ONE JSON line.  Libraries write to the C-level stdout too (NCCL prints its version banner with
+# printf when NCCL_DEBUG is set on the box), so file descriptor 1 is pointed at stderr for the whole run and the
+# result line is written to the saved descriptor at the end.
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+_RESULT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj):
+    sys.stdout.flush()
+    os.write(_RESULT_FD, (json.dumps(obj) + "\n").encode())
+
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 CKPT = os.path.join(ROOT, "tests", "golden", "thermompnn_default_slim.npz")
@@ -190,7 +203,7 @@ def run_reference(args, rank, world):
     value = muts / (ms / 1e3)
     sample = (f"per step: full ProteinMPNN pass + {n_sample} of {muts // len(pdbs)} per-mutation head iterations per protein on "
               f"{len(pdbs)} protein(s), head time scaled to the full mutation list")
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "mutations/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": {"workload": desc, "host": "cpu"},
@@ -382,7 +395,7 @@ def run_ours(args, rank, world, local_rank):
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "kernels": kern,
             "wall_s_timed_region": t_wall,
         }
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
