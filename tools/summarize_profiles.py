@@ -107,7 +107,7 @@ if __name__ == "__main__":
     full_capture("c2", f"ncu --set full --clock-control none --import-source on -k regex:'tc_edge_kernel|node_update' -s 45 -c 3 -o gpurun_out/{tag}_full_c2 python bench.py --steps 1 --warmup 3 --no-cpu", traffic)
     json.dump(traffic, open(os.path.join(P, f"{tag}_traffic.json"), "w"), indent=1)
     lines = []
-    for w in ("c2", "c3", "c5", "ref"):
+    for w in ("c2", "c3", "c5", "ref", "c2_2gpu"):
         bj = os.path.join(G, f"{tag}_bench_{w}.json")
         if os.path.exists(bj):
             lines.append(open(bj).read().strip())
