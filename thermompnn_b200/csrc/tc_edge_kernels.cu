@@ -118,22 +118,21 @@ __device__ __forceinline__ void publish_A_chunk(uint32_t lane_addr, int c, const
 enum TcKind { TC_UPD = 0, TC_ENC = 1, TC_DEC = 2 };
 
 constexpr int T2_THREADS = 352;
-constexpr int T2_NW = 3, T2_NACT = 4;
+constexpr int T2_NW_MAX = 4, T2_NACT = 4;   // weight slots: 4 in the message kernels, 3 + the output staging slab in edge_upd
 constexpr int ACT_PITCH = 36;          // floats per row of an activation chunk: 128 B of data + 16 B pad, so that thread-per-row
                                        // 16-byte reads hit 8 different bank groups per quarter-warp (9r mod 8 = r mod 8)
 constexpr uint32_t T2_HALF = 16384;   // one [128 n][32 k] tf32 plane
 
 struct __align__(1024) Tc2Smem {
-    uint8_t w[T2_NW][2 * T2_HALF];       // 96 KB  weight chunks: B_hi plane | B_lo plane
+    uint8_t w[T2_NW_MAX][2 * T2_HALF];   // 128 KB weight chunks: B_hi plane | B_lo plane (edge_upd: slot 3 = output staging)
     float act[T2_NACT][TC_ROWS * ACT_PITCH];   // 72 KB  gathered activation chunks, row pitch 144 B
-    float out[2][TC_ROWS * 32];          // 32 KB  UPD: output staging, one slab per epilogue set
     float p[2][4][HID];                  // P rows of the residues the tile touches, double-buffered by tile parity
     float wrow[2][TC_ROWS];
     float mrow[2][TC_ROWS];
     float vec[4][HID];
     float2 lnx[4][TC_ROWS];              // LayerNorm partial (mean, M2) exchange between the epilogue sets
     int jidx[TC_ROWS];
-    uint64_t w_full[T2_NW], w_empty[T2_NW];
+    uint64_t w_full[T2_NW_MAX], w_empty[T2_NW_MAX];
     uint64_t act_full[T2_NACT], act_empty[T2_NACT];
     uint64_t a_ready[8], d_ready[2];     // a_ready: one per 16-column sub-chunk of the A operand
     uint32_t tmem_base;
@@ -226,18 +225,20 @@ __device__ __forceinline__ void load_vec16(float (&v)[16], const float* p) {
 template <int KIND, int NSETS, int NAP>
 __global__ void __launch_bounds__((4 * NSETS + 2 + NAP) * 32, 1) tc_edge_kernel(const __grid_constant__ TcArgs a) {
     constexpr int STAGES = (KIND == TC_UPD) ? 3 : 2;
+    constexpr int T2_NW = (KIND == TC_UPD) ? 3 : 4;      // the weight stream is latency-bound: chunks in flight = slots - 1
     constexpr int W_MMA = 4 * NSETS, W_WPROD = 4 * NSETS + 1, W_APROD = 4 * NSETS + 2;
     constexpr int NTHREADS = (4 * NSETS + 2 + NAP) * 32, EPI_THREADS = 128 * NSETS;
     constexpr int RPL = 4 / NAP;                         // tile rows per activation-producer lane
     constexpr int SPT = 8 / NSETS;                       // sub-chunks per thread and stage
     extern __shared__ uint8_t smem_raw[];
+    if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[13] = clock64();   // kernel entry
     Tc2Smem& S = *reinterpret_cast<Tc2Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int N = a.N, num_tiles = a.num_tiles;
     const int total_rows = N * KNB;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < T2_NW; ++i) { mbar_init(&S.w_full[i], 1); mbar_init(&S.w_empty[i], 1); }
+        for (int i = 0; i < T2_NW_MAX; ++i) { mbar_init(&S.w_full[i], 1); mbar_init(&S.w_empty[i], 1); }
         for (int i = 0; i < T2_NACT; ++i) { mbar_init(&S.act_full[i], 64 * NAP); mbar_init(&S.act_empty[i], 256); }
         for (int i = 0; i < 8; ++i) mbar_init(&S.a_ready[i], 128);
         for (int i = 0; i < 2; ++i) mbar_init(&S.d_ready[i], 1);
@@ -254,8 +255,10 @@ __global__ void __launch_bounds__((4 * NSETS + 2 + NAP) * 32, 1) tc_edge_kernel(
     const uint32_t tmem = S.tmem_base;
     // PDL: everything above touched only constants, shared memory and TMEM.  The weight producer keeps to constants and
     // starts streaming at once; every other warp first waits for the kernels that wrote h_E / P / Q / E_idx.
+    if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[14] = clock64();   // setup done
     pdl_trigger();
     if (warp != W_WPROD) pdl_wait();
+    if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[15] = clock64();   // predecessor complete
 
     if (warp == W_WPROD) {
         // ---------------- weight producer ----------------
@@ -546,7 +549,7 @@ __global__ void __launch_bounds__((4 * NSETS + 2 + NAP) * 32, 1) tc_edge_kernel(
                 for (int q = 0; q < NSETS; ++q) { const float2 o = S.lnx[q][r]; const float dm = o.x - mean; m2 += o.y + MV * dm * dm; }
                 const float var = m2 * (1.0f / HID);
                 const float rstd = 1.0f / sqrtf(var + LN_EPS);
-                float* ost = &S.out[0][0];                      // [128 rows][64 cols], 16-byte chunks XOR-swizzled by row
+                float* ost = reinterpret_cast<float*>(S.w[3]);  // [128 rows][64 cols], 16-byte chunks XOR-swizzled by row
                 for (int hf = 0; hf < 2; ++hf) {
 #pragma unroll
                     for (int cc = 0; cc < SPT / 2; ++cc) {
