@@ -169,6 +169,14 @@ __device__ __forceinline__ void mma_tf32_ts_lh_init(uint32_t d_tmem, uint32_t a_
         "r"(a_tmem), "r"(desc_lo), "r"(desc_hi), "r"(idesc)
         : "memory");
 }
+// One lane of a converged warp, chosen by elect.sync.  ptxas treats a branch on this predicate as a single-thread
+// region and keeps warp-uniform operands in uniform registers; a branch on `lane == 0` instead makes it wrap every
+// tcgen05.mma in an ELECT + 4x R2UR.BROADCAST "waterfall" loop (~100 cycles per MMA instead of the pipe's 64).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 constexpr uint32_t DESC_SW128_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B
 __device__ __forceinline__ uint32_t desc_sw128_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
 

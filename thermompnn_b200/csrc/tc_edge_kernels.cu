@@ -118,13 +118,14 @@ __device__ __forceinline__ void publish_A_chunk(uint32_t lane_addr, int c, const
 enum TcKind { TC_UPD = 0, TC_ENC = 1, TC_DEC = 2 };
 
 constexpr int T2_THREADS = 352;
-constexpr int T2_NW_MAX = 4, T2_NACT = 4;   // weight slots: 4 in the message kernels, 3 + the output staging slab in edge_upd
+constexpr int T2_NW = 3, T2_NACT = 4;       // (a fourth weight slot was measured: no faster, the weight stream is not the limiter)
 constexpr int ACT_PITCH = 36;          // floats per row of an activation chunk: 128 B of data + 16 B pad, so that thread-per-row
                                        // 16-byte reads hit 8 different bank groups per quarter-warp (9r mod 8 = r mod 8)
 constexpr uint32_t T2_HALF = 16384;   // one [128 n][32 k] tf32 plane
 
 struct __align__(1024) Tc2Smem {
-    uint8_t w[T2_NW_MAX][2 * T2_HALF];   // 128 KB weight chunks: B_hi plane | B_lo plane (edge_upd: slot 3 = output staging)
+    uint8_t w[T2_NW][2 * T2_HALF];       // 96 KB  weight chunks: B_hi plane | B_lo plane
+    float out[2][TC_ROWS * 32];          // 32 KB  UPD: output staging, one slab per epilogue set
     float act[T2_NACT][TC_ROWS * ACT_PITCH];   // 72 KB  gathered activation chunks, row pitch 144 B
     float p[2][4][HID];                  // P rows of the residues the tile touches, double-buffered by tile parity
     float wrow[2][TC_ROWS];
@@ -132,7 +133,7 @@ struct __align__(1024) Tc2Smem {
     float vec[4][HID];
     float2 lnx[4][TC_ROWS];              // LayerNorm partial (mean, M2) exchange between the epilogue sets
     int jidx[TC_ROWS];
-    uint64_t w_full[T2_NW_MAX], w_empty[T2_NW_MAX];
+    uint64_t w_full[T2_NW], w_empty[T2_NW];
     uint64_t act_full[T2_NACT], act_empty[T2_NACT];
     uint64_t a_ready[8], d_ready[2];     // a_ready: one per 16-column sub-chunk of the A operand
     uint32_t tmem_base;
@@ -225,7 +226,6 @@ __device__ __forceinline__ void load_vec16(float (&v)[16], const float* p) {
 template <int KIND, int NSETS, int NAP>
 __global__ void __launch_bounds__((4 * NSETS + 2 + NAP) * 32, 1) tc_edge_kernel(const __grid_constant__ TcArgs a) {
     constexpr int STAGES = (KIND == TC_UPD) ? 3 : 2;
-    constexpr int T2_NW = (KIND == TC_UPD) ? 3 : 4;      // the weight stream is latency-bound: chunks in flight = slots - 1
     constexpr int W_MMA = 4 * NSETS, W_WPROD = 4 * NSETS + 1, W_APROD = 4 * NSETS + 2;
     constexpr int NTHREADS = (4 * NSETS + 2 + NAP) * 32, EPI_THREADS = 128 * NSETS;
     constexpr int RPL = 4 / NAP;                         // tile rows per activation-producer lane
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__((4 * NSETS + 2 + NAP) * 32, 1) tc_edge_kernel(
     const int total_rows = N * KNB;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < T2_NW_MAX; ++i) { mbar_init(&S.w_full[i], 1); mbar_init(&S.w_empty[i], 1); }
+        for (int i = 0; i < T2_NW; ++i) { mbar_init(&S.w_full[i], 1); mbar_init(&S.w_empty[i], 1); }
         for (int i = 0; i < T2_NACT; ++i) { mbar_init(&S.act_full[i], 64 * NAP); mbar_init(&S.act_empty[i], 256); }
         for (int i = 0; i < 8; ++i) mbar_init(&S.a_ready[i], 128);
         for (int i = 0; i < 2; ++i) mbar_init(&S.d_ready[i], 1);
@@ -275,11 +275,10 @@ __global__ void __launch_bounds__((4 * NSETS + 2 + NAP) * 32, 1) tc_edge_kernel(
     } else if (warp == W_MMA) {
         // ---------------- MMA issuer: one 16-column sub-chunk (2 K-steps) at a time, as the epilogue publishes them ----
         // The whole warp runs the loop so that every operand is warp-uniform (lives in uniform registers); only the
-        // tcgen05 instructions themselves are predicated on lane 0.  Computing operands inside an `if (lane == 0)` region
+        // tcgen05 instructions themselves sit under `if (elect_one())`.  Computing operands inside an `if (lane == 0)` region
         // makes the compiler wrap each UTCHMMA in a ~10-instruction uniform-register "waterfall".
         {
             const uint32_t idesc = make_idesc_tf32(128, 128);
-            const bool leader = lane == 0;
             const uint32_t tmem = __shfl_sync(0xffffffffu, S.tmem_base, 0);   // a value the compiler KNOWS is warp-uniform
             uint32_t it = 0, g = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
@@ -301,7 +300,7 @@ __global__ void __launch_bounds__((4 * NSETS + 2 + NAP) * 32, 1) tc_edge_kernel(
                             const bool first = (c == 0) && (half == 0);
                             // per 16-column sub-chunk: the two small correction products first, then hi.hi; descriptor
                             // offsets are compile-time (16-byte units: K-step 32 B -> +2, second half +4, lo plane +1024)
-                            if (leader) {
+                            if (elect_one()) {
                                 if (first) mma_tf32_ts_lh_init(d, alo, bh, DESC_SW128_HI, idesc);
                                 else mma_tf32_ts_lh(d, alo, bh + half * 4, DESC_SW128_HI, idesc);
                                 mma_tf32_ts_lh(d, ahi, bh + 1024 + half * 4, DESC_SW128_HI, idesc);
@@ -312,9 +311,9 @@ __global__ void __launch_bounds__((4 * NSETS + 2 + NAP) * 32, 1) tc_edge_kernel(
                             }
                             __syncwarp();
                         }
-                        if (leader) mma_commit(&S.w_empty[sw]);
+                        if (elect_one()) mma_commit(&S.w_empty[sw]);
                     }
-                    if (leader) mma_commit(&S.d_ready[g & 1]);
+                    if (elect_one()) mma_commit(&S.d_ready[g & 1]);
                     TC_STAMP(g / STAGES, 25 + 2 * l);
                 }
         }
@@ -549,7 +548,7 @@ __global__ void __launch_bounds__((4 * NSETS + 2 + NAP) * 32, 1) tc_edge_kernel(
                 for (int q = 0; q < NSETS; ++q) { const float2 o = S.lnx[q][r]; const float dm = o.x - mean; m2 += o.y + MV * dm * dm; }
                 const float var = m2 * (1.0f / HID);
                 const float rstd = 1.0f / sqrtf(var + LN_EPS);
-                float* ost = reinterpret_cast<float*>(S.w[3]);  // [128 rows][64 cols], 16-byte chunks XOR-swizzled by row
+                float* ost = &S.out[0][0];                      // [128 rows][64 cols], 16-byte chunks XOR-swizzled by row
                 for (int hf = 0; hf < 2; ++hf) {
 #pragma unroll
                     for (int cc = 0; cc < SPT / 2; ++cc) {
@@ -706,12 +705,11 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tc_edge_feat_kernel(TcFeatArgs 
                 }
         }
     } else if (warp == 8) {
-        {                                                 // MMA issuer (whole warp runs the loop; lane 0 issues)
+        {                                                 // MMA issuer (whole warp runs the loop; one elected lane issues)
             // GEMM1 (416 deep): hi.hi products accumulate in D0, the small corrections (lo.hi, hi.lo) in D1 -- with 13
             // K-chunks the truncating accumulator would otherwise lose them against the large partial sums (this GEMM was
             // the whole end-to-end error of the tensor-core path).  The epilogue adds D0 + D1.  GEMM2 (W_e) -> D1.
             const uint32_t idesc = make_idesc_tf32(128, 128);
-            const bool leader = lane == 0;
             const uint32_t tmem = __shfl_sync(0xffffffffu, S.tmem_base, 0);   // warp-uniform for the compiler
             uint32_t it = 0, apar = 0;                        // apar: bit s = parity of a_ready[s]'s next completion
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
@@ -728,7 +726,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tc_edge_feat_kernel(TcFeatArgs 
                         tc_fence_after();
                         const uint32_t bh = desc_sw128_lo(smem_u32(S.wring[slot]));
                         const uint32_t ahi = tmem + COL_AHI + as * 32, alo = tmem + COL_ALO + as * 32;
-                        if (leader) {
+                        if (elect_one()) {
                             if (c == 0) mma_tf32_ts_lh_init(d_corr, alo, bh, DESC_SW128_HI, idesc);
                             else mma_tf32_ts_lh(d_corr, alo, bh, DESC_SW128_HI, idesc);
                             mma_tf32_ts_lh(d_corr, ahi, bh + 1024, DESC_SW128_HI, idesc);
@@ -746,7 +744,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tc_edge_feat_kernel(TcFeatArgs 
                         }
                         __syncwarp();
                     }
-                    if (leader) mma_commit(&S.d_ready[l]);
+                    if (elect_one()) mma_commit(&S.d_ready[l]);
                 }
         }
     } else if (warp == 10) {
