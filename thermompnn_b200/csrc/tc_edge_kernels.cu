@@ -136,6 +136,7 @@ struct __align__(1024) Tc2Smem {
     uint64_t w_full[T2_NW], w_empty[T2_NW];
     uint64_t act_full[T2_NACT], act_empty[T2_NACT];
     uint64_t a_ready[8], d_ready[2];     // a_ready: one per 16-column sub-chunk of the A operand
+    uint64_t meta_full[2];               // wrow / mrow / p of a tile (by tile parity) are in place
     uint32_t tmem_base;
 };
 
@@ -221,8 +222,9 @@ __device__ __forceinline__ void load_vec16(float (&v)[16], const float* p) {
 }
 
 // NSETS epilogue sets of four warps: set s handles the 16-column sub-chunks sc with sc % NSETS == s.
-// (NSETS = 4 was measured no faster than 2; with 4, sets 2-3 never wait on chunk 0 of a tile, whose barrier also
-// publishes S.p / wrow / mrow, so that variant would need an extra wait before it is used.)
+// (Four sets -- 16 epilogue warps, two sub-chunks per thread and stage -- measured 8 % SLOWER than two: the epilogue is
+// bound by its instruction count, not by per-thread latency, and four sets publish their sub-chunks in two bursts,
+// which the MMA warp follows less closely than the finer interleave of two sets.)
 template <int KIND, int NSETS, int NAP>
 __global__ void __launch_bounds__((4 * NSETS + 2 + NAP) * 32, 1) tc_edge_kernel(const __grid_constant__ TcArgs a) {
     constexpr int STAGES = (KIND == TC_UPD) ? 3 : 2;
@@ -240,6 +242,7 @@ __global__ void __launch_bounds__((4 * NSETS + 2 + NAP) * 32, 1) tc_edge_kernel(
     if (threadIdx.x == 0) {
         for (int i = 0; i < T2_NW; ++i) { mbar_init(&S.w_full[i], 1); mbar_init(&S.w_empty[i], 1); }
         for (int i = 0; i < T2_NACT; ++i) { mbar_init(&S.act_full[i], 64 * NAP); mbar_init(&S.act_empty[i], 256); }
+        for (int i = 0; i < 2; ++i) mbar_init(&S.meta_full[i], 64 * NAP);
         for (int i = 0; i < 8; ++i) mbar_init(&S.a_ready[i], 128);
         for (int i = 0; i < 2; ++i) mbar_init(&S.d_ready[i], 1);
         fence_barrier_init();
@@ -354,16 +357,8 @@ __global__ void __launch_bounds__((4 * NSETS + 2 + NAP) * 32, 1) tc_edge_kernel(
                 mbar_arrive_expect_tx(&S.act_full[s], TC_ROWS * 32 * 4);
                 tma_load_2d(S.act[s], &a.tm_hE, c * 32, row0, &S.act_full[s]);
             }
-            if (with_p_buf >= 0) {
-                const int node_lo = row0 / KNB;
-#pragma unroll
-                for (int i = pw * RPL; i < (pw + 1) * RPL; ++i) {
-                    int node = node_lo + i; node = node < N ? node : N - 1;
-                    cp_async16_ca(&S.p[with_p_buf][i][lane * 4], a.P + (size_t)node * a.p_stride + lane * 4);
-                }
-            }
             cp_async_arrive_noinc(&S.act_full[s]);          // fires when this lane's copies have landed
-            if (!tma_lane) mbar_arrive(&S.act_full[s]);     // releases this lane's plain stores (wrow/mrow)
+            if (!tma_lane) mbar_arrive(&S.act_full[s]);
             ++k;
         };
         // metadata of a tile (weights / masks per row) + its four input chunks; returns the neighbour rows in jnext
@@ -383,7 +378,17 @@ __global__ void __launch_bounds__((4 * NSETS + 2 + NAP) * 32, 1) tc_edge_kernel(
                 }
                 jnext[i] = j; S.wrow[mb][r] = w; S.mrow[mb][r] = mi;
             }
-            for (int c = 0; c < 4; ++c) chunk(row0, c, false, c == 0 ? (int)mb : -1);
+            {   // P rows of the (up to 4) residues the tile touches; then publish the tile's metadata on its own barrier
+                const int node_lo = row0 / KNB;
+#pragma unroll
+                for (int i = pw * RPL; i < (pw + 1) * RPL; ++i) {
+                    int node = node_lo + i; node = node < N ? node : N - 1;
+                    cp_async16_ca(&S.p[mb][i][lane * 4], a.P + (size_t)node * a.p_stride + lane * 4);
+                }
+                cp_async_arrive_noinc(&S.meta_full[mb]);    // P rows landed
+                mbar_arrive(&S.meta_full[mb]);              // wrow / mrow stores released
+            }
+            for (int c = 0; c < 4; ++c) chunk(row0, c, false, -1);
         };
         uint32_t ti = 0;
         int tile = blockIdx.x;
@@ -440,6 +445,7 @@ __global__ void __launch_bounds__((4 * NSETS + 2 + NAP) * 32, 1) tc_edge_kernel(
             const uint32_t mb = ti & 1;
             int node_l = row / KNB - row0 / KNB;
             node_l = node_l > 3 ? 3 : node_l;
+            mbar_wait(&S.meta_full[mb], (ti >> 1) & 1);
             const float w_r = S.wrow[mb][r], m_i = S.mrow[mb][r];
             EPI_STAMP(0);
             // ---- stage 1: gathered projections, GELU
