@@ -1,12 +1,15 @@
 // Tensor-core (tcgen05) generation of the per-edge kernels.
 //
 // One CTA works on tiles of 128 consecutive edge rows (rows of the [N*48][128] h_E array; tiles ignore residue
-// boundaries).  Warp roles:
-//   warps 0-3  epilogue: thread t of warp w owns edge row 32w+t = TMEM lane 32w+t.  It turns each accumulator
-//              chunk into the next GEMM's A operand (bias / gathered projections, GELU, hi/lo split, tcgen05.st)
-//   warp 4     lane 0 issues tcgen05.mma (kind::tf32, A from TMEM, B from shared memory), owns the TMEM allocation
-//   warp 5     lane 0 streams weight chunks (pre-split, pre-swizzled 32 KB images) through a 3-slot ring (bulk copy)
-//   warp 6     gathers activations with cp.async: the h_E tile, the P rows and the neighbours' Q rows
+// boundaries).  Warp roles of tc_edge_kernel (448 threads; tc_edge_feat_kernel is laid out the same way with its own
+// producers):
+//   warps 0-7    epilogue, two sets of four: thread t of warp w owns edge row 32(w%4)+t = TMEM lane.  It turns each
+//                16-column accumulator sub-chunk into the next GEMM's A operand (bias / gathered projections, GELU,
+//                hi/lo split, tcgen05.st); set s takes the sub-chunks of parity s
+//   warp 8       one elected lane issues tcgen05.mma (kind::tf32, A from TMEM, B from shared memory); owns TMEM
+//   warp 9       lane 0 streams weight chunks (pre-split, pre-swizzled 32 KB images) through a 3-slot ring (bulk copy)
+//   warps 10-13  activation producers: h_E chunks by TMA tensor-map copies, neighbours' Q rows by cp.async gathers,
+//                per-tile metadata (edge weights, masks, P rows)
 //
 // TMEM (512 columns): D0 | D1 | A_hi | A_lo, 128 columns each.  The accumulator is double buffered so that
 // stage l+1's MMAs (fed chunk by chunk as the epilogue of stage l produces A) run underneath that epilogue.
@@ -109,8 +112,7 @@ __device__ __forceinline__ void publish_A_chunk(uint32_t lane_addr, int c, const
 // into Spart[residue][0..2][128]; node_update adds the three parts in order, so the neighbour sum is deterministic
 // and independent of where the residue sits in the batch.  W3 is applied there, after the sum.
 //
-// Warp roles (352 threads): warps 0-7 epilogue (two sets of four; set s handles 32-column chunks c with c%2 == s,
-// thread = edge row = TMEM lane), warp 8 MMA issuer, warp 9 weight producer, warp 10 activation producer.
+// Warp roles: see the top of the file.
 // Everything gathered per row (h_E input, Q_j, the residual) flows through ONE ring of [128 rows][32 cols] chunks.
 // MMA schedule: K-chunk by K-chunk as the epilogue publishes them (short tail after the last chunk); inside a chunk
 // the two small correction products (A_lo.B_hi, A_hi.B_lo) go first, then A_hi.B_hi.
