@@ -546,11 +546,12 @@ __global__ void __launch_bounds__(NK_THREADS, 1) node_update_step_kernel(NodeUpd
 template <int NT>
 __global__ void __launch_bounds__(NK_THREADS, 1) head_kernel(HeadArgs a) {
     constexpr int NJ = NT / 4;
+    constexpr int XP3 = 3 * HID + 4;             // padded row pitch of the 384-wide inputs (see tile_fma)
     extern __shared__ __align__(16) float smem[];
     float* ring = smem;
-    float* x = ring + 2 * STEP_FLOATS;           // [NT][384]; later z1 [NT][128]
-    float* y = x + NT * 3 * HID;                 // [NT][384]; later z2 [NT][128]
-    float* part = y + NT * 3 * HID;              // [4][NT][128]
+    float* x = ring + 2 * STEP_FLOATS;           // [NT][XP3]; later z1 [NT][XP]
+    float* y = x + NT * XP3;                     // [NT][XP3]; later z2 [NT][XP]
+    float* part = y + NT * XP3;                  // [4][NT][128]
     const int q = threadIdx.x >> 7, n = threadIdx.x & 127;
     const int node0 = blockIdx.x * NT;
     const float* wb = a.weights;
@@ -561,30 +562,30 @@ __global__ void __launch_bounds__(NK_THREADS, 1) head_kernel(HeadArgs a) {
     for (int i = threadIdx.x; i < NT * HID; i += NK_THREADS) {
         int t = i / HID, c = i % HID, node = node0 + t;
         bool ok = node < a.N;
-        x[t * 3 * HID + c] = ok ? a.dec_last[(size_t)node * HID + c] : 0.f;
-        x[t * 3 * HID + HID + c] = ok ? a.dec_prev[(size_t)node * HID + c] : 0.f;
-        x[t * 3 * HID + 2 * HID + c] = ok ? __ldg(wb + a.Ws + (size_t)a.S[node] * HID + c) : 0.f;
+        x[t * XP3 + c] = ok ? a.dec_last[(size_t)node * HID + c] : 0.f;
+        x[t * XP3 + HID + c] = ok ? a.dec_prev[(size_t)node * HID + c] : 0.f;
+        x[t * XP3 + 2 * HID + c] = ok ? __ldg(wb + a.Ws + (size_t)a.S[node] * HID + c) : 0.f;
     }
     float res[NJ];
     for (int blk = 0; blk < 3; ++blk) {
-        phase_ksplit<NT>(res, ws, 3, x, 3 * HID, part);
+        phase_ksplit_t<NJ>(res, ws, 3, x, XP3, part);
         const float b = __ldg(wb + a.la_b + blk * HID + n);
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) y[(q + 4 * j) * 3 * HID + blk * HID + n] = fmaxf(res[j] + b, 0.f);
+        for (int j = 0; j < NJ; ++j) y[(q + 4 * j) * XP3 + blk * HID + n] = fmaxf(res[j] + b, 0.f);
     }
-    phase_ksplit<NT>(res, ws, 3, y, 3 * HID, part);
+    phase_ksplit_t<NJ>(res, ws, 3, y, XP3, part);
     {
         const float b = n < 64 ? __ldg(wb + a.m1_b + n) : 0.f;
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) x[(q + 4 * j) * HID + n] = fmaxf(res[j] + b, 0.f);   // z1 (columns >= 64 are 0)
+        for (int j = 0; j < NJ; ++j) x[(q + 4 * j) * XP + n] = fmaxf(res[j] + b, 0.f);   // z1 (columns >= 64 are 0)
     }
-    phase_ksplit<NT>(res, ws, 1, x, HID, part);
+    phase_ksplit_t<NJ>(res, ws, 1, x, XP, part);
     {
         const float b = n < 32 ? __ldg(wb + a.m2_b + n) : 0.f;
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) y[(q + 4 * j) * HID + n] = fmaxf(res[j] + b, 0.f);   // z2 (columns >= 32 are 0)
+        for (int j = 0; j < NJ; ++j) y[(q + 4 * j) * XP + n] = fmaxf(res[j] + b, 0.f);   // z2 (columns >= 32 are 0)
     }
-    phase_ksplit<NT>(res, ws, 1, y, HID, part);
+    phase_ksplit_t<NJ>(res, ws, 1, y, XP, part);
     if (n < 21) {
         const float b = __ldg(wb + a.m3_b + n), sc = __ldg(wb + a.ddg), sh = __ldg(wb + a.ddg + 1);
 #pragma unroll
@@ -724,7 +725,7 @@ template <int NT> static size_t smem_head_cluster() {
     return sizeof(float) * (NC_SLOTS * WCHUNK_FLOATS + 2 * NT * 3 * HID + 2 * NT * HID);
 }
 template <int NT> static size_t smem_head() {
-    return sizeof(float) * (2 * STEP_FLOATS + 2 * NT * 3 * HID + 4 * NT * HID);
+    return sizeof(float) * (2 * STEP_FLOATS + 2 * NT * (3 * HID + 4) + 4 * NT * HID);
 }
 
 cudaError_t node_kernels_init() {
@@ -734,7 +735,7 @@ cudaError_t node_kernels_init() {
     if ((e = cudaFuncSetAttribute(node_update_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_node_update<12>())) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(node_update_step_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_node_update_step<16>())) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(node_update_step_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_node_update_step<32>())) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(head_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_head<8>())) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(head_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_head<16>())) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(head_cluster_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_head_cluster<8>())) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(head_cluster_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_head_cluster<12>())) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(head_cluster_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_head_cluster<16>())) != cudaSuccess) return e;
@@ -768,7 +769,7 @@ void launch_head(const HeadArgs& a, int sms, cudaStream_t st) {
     } else if (4 * ((N + 15) / 16) <= sms) {
         launch_pdl(head_cluster_kernel<16>, dim3(4 * ((N + 15) / 16)), dim3(NC_THREADS), smem_head_cluster<16>(), st, a);
     } else {
-        launch_pdl(head_kernel<8>, dim3((N + 7) / 8), dim3(NK_THREADS), smem_head<8>(), st, a);
+        launch_pdl(head_kernel<16>, dim3((N + 15) / 16), dim3(NK_THREADS), smem_head<16>(), st, a);
     }
 }
 
