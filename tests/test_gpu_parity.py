@@ -111,6 +111,15 @@ def test_large_batch_equals_single_runs(gpu_model):
         assert np.array_equal(batch[i], gpu_model.head_tables([pdbs[i]])[0]), i
 
 
+def test_repeated_runs_are_bit_identical(gpu_model):
+    """No atomics, no timing-dependent summation order: the same call gives the same bits every time."""
+    pdbs = [synth(257, 21), synth(64, 22), synth(511, 23)]
+    ref = gpu_model.head_tables(pdbs)
+    for _ in range(5):
+        for a, b in zip(ref, gpu_model.head_tables(pdbs)):
+            assert np.array_equal(a, b)
+
+
 def test_against_oracle_on_fresh_inputs(gpu_model, oracle_weights):
     """Inputs with no committed fixture: the oracle is the checker (edge cases: tiny, K=L, gaps, two chains)."""
     from oracle import thermompnn_oracle as O
