@@ -456,16 +456,19 @@ __global__ void __launch_bounds__((4 * NSETS + 2 + NAP) * 32, 1) tc_edge_kernel(
             EPI_STAMP(2);
             {
                 const uint32_t dcol = (g & 1) ? COL_D1 : COL_D0;
+                uint32_t accb[2][16];                          // accumulator loads run one sub-chunk ahead of the math
+                tmem_ld16(lane_addr + dcol + set * 16, accb[0]);
+#pragma unroll
                 for (int c = 0; c < SPT; ++c) {
                     const int sc = set + NSETS * c;
-                    uint32_t acc[16];
-                    tmem_ld16(lane_addr + dcol + sc * 16, acc);
+                    uint32_t (&acc)[16] = accb[c & 1];
                     const float* chunk = act_wait(kc + (sc >> 1));
                     float qv[16], pv[16], v[16];
                     load_act16(qv, chunk, r, sc & 1);
                     act_release(kc + (sc >> 1));
                     load_vec16(pv, &S.p[mb][node_l][sc * 16]);
                     tmem_wait_ld();
+                    if (c + 1 < SPT) tmem_ld16(lane_addr + dcol + (sc + NSETS) * 16, accb[(c + 1) & 1]);
 #pragma unroll
                     for (int j = 0; j < 16; j += 2) {      // packed pairs: same per-lane operation order as the scalar form
                         const f32x2 a2 = pk2(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]));
@@ -486,13 +489,16 @@ __global__ void __launch_bounds__((4 * NSETS + 2 + NAP) * 32, 1) tc_edge_kernel(
                 EPI_STAMP(4);
                 {
                     const uint32_t dcol = (g & 1) ? COL_D1 : COL_D0;
+                    uint32_t accb[2][16];
+                    tmem_ld16(lane_addr + dcol + set * 16, accb[0]);
+#pragma unroll
                     for (int c = 0; c < SPT; ++c) {
                         const int sc = set + NSETS * c;
-                        uint32_t acc[16];
-                        tmem_ld16(lane_addr + dcol + sc * 16, acc);
+                        uint32_t (&acc)[16] = accb[c & 1];
                         float bv[16], v[16];
                         load_vec16(bv, &S.vec[0][sc * 16]);
                         tmem_wait_ld();
+                        if (c + 1 < SPT) tmem_ld16(lane_addr + dcol + (sc + NSETS) * 16, accb[(c + 1) & 1]);
 #pragma unroll
                         for (int j = 0; j < 16; j += 2)
                             upk2(gelu_fast2(add2(pk2(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1])), pk2(bv[j], bv[j + 1]))), v[j], v[j + 1]);
