@@ -521,16 +521,19 @@ __global__ void __launch_bounds__((4 * NSETS + 2 + NAP) * 32, 1) tc_edge_kernel(
             if (KIND == TC_UPD) {
                 // ---- final: + b13 + residual, LayerNorm over the row (two threads per row), direct 64-byte row stores
                 float shift = 0.f, s1 = 0.f, s2 = 0.f;
+                uint32_t accb[2][16];
+                tmem_ld16(lane_addr + dcol + set * 16, accb[0]);
+#pragma unroll
                 for (int c = 0; c < SPT; ++c) {
                     const int sc = set + NSETS * c;
-                    uint32_t acc[16];
-                    tmem_ld16(lane_addr + dcol + sc * 16, acc);
+                    uint32_t (&acc)[16] = accb[c & 1];
                     const float* chunk = act_wait(kc + (sc >> 1));
                     float old[16], bv[16];
                     load_act16_sw(old, chunk, r, sc & 1);
                     act_release(kc + (sc >> 1));
                     load_vec16(bv, &S.vec[1][sc * 16]);
                     tmem_wait_ld();
+                    if (c + 1 < SPT) tmem_ld16(lane_addr + dcol + (sc + NSETS) * 16, accb[(c + 1) & 1]);
                     if (c == 0) shift = __uint_as_float(acc[0]) + bv[0] + old[0];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
@@ -602,14 +605,16 @@ __global__ void __launch_bounds__((4 * NSETS + 2 + NAP) * 32, 1) tc_edge_kernel(
                 const int node = sb / 3, part = sb - node * 3;
                 for (int c = 0; c < SPT; c += 2) {                     // two 16-column sub-chunks per transpose-reduce
                     float gv[32];
+                    uint32_t acc2[2][16];                              // both sub-chunks' loads in flight before the first wait
+                    tmem_ld16(lane_addr + dcol + (NSETS * c + set) * 16, acc2[0]);
+                    tmem_ld16(lane_addr + dcol + (NSETS * (c + 1) + set) * 16, acc2[1]);
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int sc = NSETS * (c + h) + set;
-                        uint32_t acc[16];
-                        tmem_ld16(lane_addr + dcol + sc * 16, acc);
+                        uint32_t (&acc)[16] = acc2[h];
                         float bv[16];
                         load_vec16(bv, &S.vec[0][sc * 16]);
-                        tmem_wait_ld();
+                        if (h == 0) tmem_wait_ld();
 #pragma unroll
                         for (int j = 0; j < 16; j += 2) {
                             float g0, g1;
