@@ -94,3 +94,19 @@ def test_synth_is_seeded_and_pdb_like():
     ca = np.asarray(a["coords_chain_A"]["CA_chain_A"])
     assert np.allclose(np.linalg.norm(np.diff(ca, axis=0), axis=1), 3.8, atol=2e-3)
     assert np.array_equal(ca, np.round(ca, 3))
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py contract: exactly one line on stdout, a JSON object with the driver's keys (the CPU arm runs anywhere)."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "config",
+              "e2e", "cpu_baseline"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 0
