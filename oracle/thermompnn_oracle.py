@@ -229,21 +229,32 @@ def _la_center(w):
     return w["light_attention.feature_convolution.weight"][:, :, 4]
 
 
-def head_table(w, hidden, h_S):
+def head_table(w, hidden, h_S, num_final_layers: int = 2, lightattn: bool = True):
     """All 21 head outputs at every position, [L,21].
 
     ``TransferModel.forward`` (transfer_model.py:96-116) evaluated once per
-    position instead of once per mutation.  LightAttention on a length-1
+    position instead of once per mutation, for any ``cfg.model`` (``num_final_layers``
+    decoder states, optional LightAttention, the ``both_out`` MLP found in ``w``;
+    transfer_model.py:45-73).  LightAttention on a length-1
     sequence (:107-108, :148-155) reduces to its centre tap: the k=9, pad=4
     convolution only multiplies zeros elsewhere, and the softmax over a length-1
     axis is 1.
     """
-    x = torch.cat([hidden[0], hidden[1], h_S], -1)           # :82-83, :96-103
-    y = F.linear(x, _la_center(w), w["light_attention.feature_convolution.bias"])
-    z = y
-    for i in (1, 3, 5):                                       # both_out = (ReLU, Linear) x3, :67-71
+    x = torch.cat(list(hidden[:num_final_layers]) + [h_S], -1)   # :82-83, :96-103
+    z = x
+    if lightattn:
+        z = F.linear(x, _la_center(w), w["light_attention.feature_convolution.bias"])
+    i = 1
+    while f"both_out.{i}.weight" in w:                            # both_out = (ReLU, Linear)*, :67-71
         z = _lin(w, f"both_out.{i}", F.relu(z))
+        i += 2
     return z * w["ddg_out.weight"].reshape(()) + w["ddg_out.bias"].reshape(())   # :73, :110-111
+
+
+def log_probs(w, h_V_last):
+    """ProteinMPNN's output layer (protein_mpnn_utils.py:1275-1276): log_softmax(W_out h_V), [L,21]; what
+    ``ProteinMPNNBaseline`` reads (analysis/thermompnn_benchmarking.py:52-58)."""
+    return F.log_softmax(_lin(w, "prot_mpnn.W_out", h_V_last), dim=-1)
 
 
 def head_per_mutation(w, hidden, h_S, position: int, wt: int, mut: int):
@@ -273,7 +284,8 @@ def cast_weights(w: Dict[str, "torch.Tensor|np.ndarray"], dtype=torch.float32):
     return {k: torch.as_tensor(np.asarray(v)).to(dtype) for k, v in w.items()}
 
 
-def ssm_table(w, pdb: dict, dtype=torch.float32, trace: Optional[dict] = None):
+def ssm_table(w, pdb: dict, dtype=torch.float32, trace: Optional[dict] = None, num_final_layers: int = 2,
+              lightattn: bool = True):
     """Site-saturation table for one protein.
 
     Returns (T [L,21], ddG [L,20], S [L]) with ``ddG[i,a] = T[i,a] - T[i,S_i]``
@@ -286,8 +298,10 @@ def ssm_table(w, pdb: dict, dtype=torch.float32, trace: Optional[dict] = None):
         mt = torch.from_numpy(mask).to(dtype)
         St = torch.from_numpy(S)
         hidden, h_S = mpnn_forward(w, Xt, St, mt, torch.from_numpy(ridx), torch.from_numpy(cenc), trace=trace)
-        T = head_table(w, hidden, h_S)
+        T = head_table(w, hidden, h_S, num_final_layers, lightattn)
         ddg = T[:, :20] - torch.gather(T, 1, St[:, None])
+        if trace is not None:
+            trace["log_probs"] = log_probs(w, hidden[0])
     if trace is not None:
         trace["h_S"] = h_S
         trace["T"] = T

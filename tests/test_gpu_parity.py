@@ -13,6 +13,9 @@ from thermompnn_b200.synth import synth, synth_multichain
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
+# Small and large batches may run different (individually batch-invariant) forms of the per-residue kernels; each form is
+# within TOL of the reference, and they agree with each other to fp32 rounding.  0 = the forms are bit-identical.
+LARGE_VS_SMALL_TOL = 0.0
 
 
 def _sets_equal(a, b):
@@ -103,12 +106,18 @@ def test_ragged_batch_equals_single_runs(gpu_model):
 
 def test_large_batch_equals_single_runs(gpu_model):
     """Same definition at a size that takes the large-batch kernel forms (many tiles per SM in the edge kernels, the
-    32-residue node-update blocks): 12 000 residues in one call, spot-checked bit for bit against single-protein calls."""
+    large-batch node-update form): 12 000 residues in one call, spot-checked against single-protein calls, and bit for
+    bit against a different large batch holding the same proteins (results never depend on what else is in the batch)."""
     pdbs = [synth(300, 500 + i) for i in range(36)] + [synth(150 + 37 * i, 900 + i) for i in range(6)]
     assert sum(len(p["seq"]) for p in pdbs) >= 2 * 148 * 32
     batch = gpu_model.head_tables(pdbs)
     for i in (0, 17, 35, 36, 41):
-        assert np.array_equal(batch[i], gpu_model.head_tables([pdbs[i]])[0]), i
+        single = gpu_model.head_tables([pdbs[i]])[0]
+        assert np.abs(batch[i] - single).max() <= LARGE_VS_SMALL_TOL, i
+    other = [synth(211, 77)] + pdbs[::-1] + [synth(64, 78)]
+    batch2 = gpu_model.head_tables(other)[1:-1][::-1]
+    for a, b in zip(batch, batch2):
+        assert np.array_equal(a, b)
 
 
 def test_repeated_runs_are_bit_identical(gpu_model):
@@ -185,3 +194,214 @@ def test_sharded_tables_single_rank(gpu_model):
     out = sharded_tables(pdbs, gpu_model.head_tables)
     for a, b in zip(out, gpu_model.head_tables(pdbs)):
         assert np.array_equal(a, b)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# round 2: configurations with no parity evidence before -- long proteins, Megascale-shaped batches --
+# and the new outputs / entry points
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["synth600", "synth2000"])
+def test_long_proteins_match_reference(name, gpu_model, gpu_baseline):
+    """L > 512 takes the k-NN kernel's shared-memory row path; L = 2000 is BASELINE configs[4]'s protein.  Neighbour
+    SETS equal the reference's for every residue, ddG and ProteinMPNN log_probs within tolerance."""
+    d, pdb = load_case(name)
+    eng = gpu_model._get_engine()
+    ddg = gpu_model.ssm_tables([pdb])[0]
+    E_idx = eng.fetch("E_idx")
+    assert _sets_equal(E_idx, d["E_idx"])
+    assert (E_idx[:, 0] == np.arange(len(pdb["seq"]))).all()
+    err = np.abs(ddg - d["ddG"]).max()
+    print(f"{name}: max |ddG_gpu - ddG_ref| = {err:.2e}")
+    assert err <= TOL
+    lp = gpu_baseline.log_prob_tables([pdb])[0]
+    assert np.abs(lp - d["log_probs"]).max() <= TOL
+
+
+def test_c4_shaped_batch_matches_reference(gpu_model):
+    """BASELINE configs[3]'s regime: many small proteins (L 32..72, half with K = L < 48) in ONE call."""
+    from conftest import c4_batch
+    d, pdbs = c4_batch()
+    assert len(pdbs) >= 64 and (d["lengths"] < 48).sum() >= 30
+    tables = gpu_model.ssm_tables(pdbs)
+    got = np.concatenate(tables, 0)
+    err = np.abs(got - d["ddG"]).max()
+    print(f"c4 batch ({len(pdbs)} proteins, {got.shape[0]} residues): max |ddG_gpu - ddG_ref| = {err:.2e}")
+    assert err <= TOL
+    eng = gpu_model._get_engine()
+    E_idx = eng.fetch("E_idx")
+    o = 0
+    for L in d["lengths"]:
+        K = min(48, int(L))
+        blk = E_idx[o:o + L]
+        assert (blk[:, K:] == -1).all() and (blk[:, :K] >= o).all() and (blk[:, :K] < o + L).all()   # neighbours stay inside the protein
+        if L <= 48:
+            assert all(set(r[:K].tolist()) == set(range(o, o + L)) for r in blk)
+        o += int(L)
+
+
+def test_log_probs_match_reference(gpu_baseline):
+    """ProteinMPNNBaseline (analysis/thermompnn_benchmarking.py:38-65): log_softmax(W_out h_V) and the forward contract."""
+    import os
+    from conftest import GOLDEN
+    ref = np.load(os.path.join(GOLDEN, "extra_logprobs.npz"))
+    names = list(ref.files)
+    pdbs = [load_case(n)[1] for n in names]
+    for n, lp in zip(names, gpu_baseline.log_prob_tables(pdbs)):           # one ragged call
+        err = np.abs(lp - ref[n]).max()
+        print(f"log_probs {n}: {err:.2e}")
+        assert err <= TOL
+    pdb = pdbs[0]
+    muts = [Mutation(0, pdb["seq"][0], "W"), None, Mutation(-1, pdb["seq"][-1], "A")]
+    with torch.no_grad():
+        out, log_probs = gpu_baseline([pdb], muts)
+    assert out[1] is None and log_probs.shape == (1, len(pdb["seq"]), 21) and log_probs.is_cuda
+    assert out[0]["ddG"].shape == (1,) and torch.equal(out[0]["ddG"], -out[0]["dTm"])
+    assert abs(out[0]["dTm"].item() - ref[names[0]][0, ALPHABET.index("W")]) <= TOL
+    assert abs(out[2]["dTm"].item() - ref[names[0]][-1, ALPHABET.index("A")]) <= TOL
+
+
+@pytest.mark.parametrize("tag", ["v1", "v2", "v3"])
+def test_cfg_variants_match_reference(tag):
+    """Other cfg.model heads (transfer_model.py:45-73) run through the generic head kernel."""
+    from conftest import cfg_variant
+    from thermompnn_b200.transfer_model import TransferModel, default_config
+    cfgd, w, ddgs = cfg_variant(tag)
+    cfg = default_config()
+    cfg.model.update(cfgd)
+    m = TransferModel(cfg, state=w).eval().cuda()
+    pdbs = {"synth90": synth(90, seed=90), "synth40": synth(40, seed=7)}
+    for pn, ref in ddgs.items():
+        err = np.abs(m.ssm_tables([pdbs[pn]])[0] - ref).max()
+        print(f"cfg {tag} {cfgd} {pn}: {err:.2e}")
+        assert err <= TOL
+
+
+def test_generic_head_equals_specialised_head(gpu_model):
+    """The default cfg through BOTH head implementations (the generic kernel is selected by a cfg that differs only
+    by a zero-effect detail: hidden_dims given as [64, 32] is the specialised path, so go through the C ABI directly)."""
+    import ctypes
+    from thermompnn_b200 import engine
+    eng = gpu_model._get_engine()
+    pdbs = [synth(70, 3), synth(33, 4)]
+    ref = gpu_model.head_tables(pdbs)
+    # same weights, declared as 2 final layers + LightAttention + hidden [64, 32, 21->21 identity]: forces the generic kernel
+    state = {n: gpu_model.weight_blob.detach().cpu().numpy()[o:o + r * c].reshape(r, c) for n, o, r, c in engine.weight_table()}
+    cfg2 = engine.ModelCfg.make(2, True, (64, 32, 21), True)
+    state["both_out.7.weight"] = np.eye(21, dtype=np.float32)
+    state["both_out.7.bias"] = np.zeros((1, 21), np.float32)
+    # ReLU in front of the identity layer would clip negative logits: shift them positive and back through ddg_out's bias
+    state["both_out.5.bias"] = state["both_out.5.bias"] + 100.0
+    state["ddg_out.bias"] = state["ddg_out.bias"] - 100.0 * state["ddg_out.weight"]
+    e2 = engine.Engine(eng.device)
+    e2.load_weights(engine.pack_weight_blob(state, cfg2), cfg2)
+    p = featurize_batch(pdbs)
+    T = e2.run(p.offsets, p.X, p.S, p.residue_idx, p.chain_enc, p.mask)
+    e2.close()
+    assert np.abs(T - np.concatenate(ref, 0)).max() <= 5e-5     # (logit + 100) - 100 costs ~1e-5 of fp32 resolution
+
+
+def test_predict_batch_and_forward(gpu_model):
+    """Listed-mutation batches: one ragged launch, results equal the per-protein reference-style calls bit for bit;
+    negative positions index from the end like upstream's tensor indexing."""
+    pdbs = [load_case("2OCJ_A")[1], synth(40, 7), synth(120, 11, gaps=[0, 17, 18, 19, 64, 119])]
+    rng = np.random.default_rng(0)
+    batch = []
+    for pdb in pdbs:
+        seq = pdb["seq"]
+        muts = [Mutation(int(i), seq[i], ALPHABET[int(rng.integers(0, 20))]) for i in rng.integers(0, len(seq), size=50) if seq[i] != "-"]
+        muts.insert(3, None)
+        batch.append(([pdb], muts))
+    with torch.no_grad():
+        outs = gpu_model.predict_batch(batch)
+        for (pdb, muts), out in zip(batch, outs):
+            single, _ = gpu_model(pdb, muts)
+            assert len(out) == len(muts) and out[3] is None
+            for a, b in zip(out, single):
+                assert (a is None and b is None) or torch.equal(a["ddG"], b["ddG"])
+        d, pdb = load_case("2OCJ_A")
+        pred, _ = gpu_model([pdb], [Mutation(-1, pdb["seq"][-1], "W"), Mutation(193, pdb["seq"][-1], "W")])
+        assert torch.equal(pred[0]["ddG"], pred[1]["ddG"])
+        assert abs(pred[0]["ddG"].item() - d["ddG"][193, ALPHABET.index("W")]) <= TOL
+        with pytest.raises(IndexError):
+            gpu_model([pdb], [Mutation(-195, "A", "C")])
+
+
+def test_graph_replay_is_bit_identical(gpu_model):
+    """Repeated calls of one shape replay a captured CUDA graph; results equal the directly launched chain."""
+    eng = gpu_model._get_engine()
+    pdbs = [synth(300, 0)]
+    p = featurize_batch(pdbs)
+    args = (p.offsets, p.X, p.S, p.residue_idx, p.chain_enc, p.mask)
+    eng.set_graphs(False)
+    ref = eng.run(*args).copy()
+    eng.set_graphs(True)
+    eng.profile_reset()
+    out = np.empty_like(ref)                           # a stable host destination (it is part of the captured chain)
+    for _ in range(4):
+        out[:] = 0
+        eng.run(*args, out=out)
+        assert np.array_equal(out, ref)
+    assert eng.graph_launch_count() >= 2
+    n_per_call = eng.launch_count() // 4
+    assert n_per_call == 18                            # replayed calls count the kernels they replay
+    # a different protein of the same length goes through the same graph (inputs are staged, not baked in)
+    p2 = featurize_batch([synth(300, 1)])
+    eng.set_graphs(False)
+    ref2 = eng.run(p2.offsets, p2.X, p2.S, p2.residue_idx, p2.chain_enc, p2.mask).copy()
+    eng.set_graphs(True)
+    for _ in range(3):
+        eng.run(*args, out=out)
+    eng.run(p2.offsets, p2.X, p2.S, p2.residue_idx, p2.chain_enc, p2.mask, out=out)
+    assert np.array_equal(out, ref2)
+
+
+def test_device_inputs_are_validated_on_the_device(gpu_model):
+    """TMPNN_IN_DEVICE: letters cannot be checked on the host; the first kernel clamps them and the call fails."""
+    from thermompnn_b200 import engine
+    eng = gpu_model._get_engine()
+    p = featurize_batch([synth(30, 1)])
+    dev = torch.device("cuda", eng.device)
+    bad = p.S.copy(); bad[7] = 21; bad[9] = -3
+    t = {k: torch.from_numpy(np.ascontiguousarray(getattr(p, k))).to(dev) for k in ("X", "residue_idx", "chain_enc", "mask")}
+    out = torch.empty((30, 21), dtype=torch.float32, device=dev)
+    for S, ok in ((bad, False), (p.S, True), (bad, False), (p.S, True)):
+        St = torch.from_numpy(S).to(dev)
+        call = lambda: eng.run(p.offsets, t["X"].data_ptr(), St.data_ptr(), t["residue_idx"].data_ptr(), t["chain_enc"].data_ptr(),
+                               t["mask"].data_ptr(), out.data_ptr(), flags=engine.IN_DEVICE | engine.OUT_DEVICE)
+        if ok:
+            call()
+            assert np.array_equal(out.cpu().numpy(), gpu_model.head_tables([synth(30, 1)])[0])
+        else:
+            with pytest.raises(engine.EngineError, match="clamped"):
+                call()
+            assert torch.isfinite(out).all()
+
+
+def test_current_device_is_left_alone(gpu_model):
+    before = torch.cuda.current_device()
+    gpu_model.head_tables([synth(20, 1)])
+    assert torch.cuda.current_device() == before
+
+
+def test_tied_masked_neighbours_are_implementation_defined(gpu_model, oracle_weights):
+    """Fewer than 48 valid residues and more masked ones than free slots: the masked candidates all tie at the row
+    maximum (protein_mpnn_utils.py:1105-1106) and torch.topk's pick among ties is unspecified (it differs between torch's
+    own CPU and CUDA kernels), while the decoder attends to masked neighbours too (no mask_attend, :1272).  So parity with
+    upstream is undefined for such inputs; what IS defined: every valid neighbour is selected, and this implementation
+    fills the remaining slots with the lowest-index masked residues, deterministically."""
+    from oracle import thermompnn_oracle as O
+    gaps = [3, 7, 11, 12, 20, 21, 22, 33, 40, 49]
+    pdb = synth(50, 77, gaps=gaps)
+    ddg = gpu_model.ssm_tables([pdb])[0]
+    eng = gpu_model._get_engine()
+    E_idx = eng.fetch("E_idx")
+    valid = np.ones(50, bool); valid[gaps] = False
+    for i in np.nonzero(valid)[0]:
+        picked = set(E_idx[i].tolist())
+        assert set(np.nonzero(valid)[0].tolist()) <= picked
+        assert sorted(j for j in picked if not valid[j]) == sorted(gaps)[:8]
+    assert np.isfinite(ddg[valid]).all() and np.isnan(ddg[~valid]).all()
+    assert np.array_equal(ddg, gpu_model.ssm_tables([pdb])[0], equal_nan=True)
+    _, ref, _ = O.ssm_table(oracle_weights, pdb)
+    print("tie-order sensitivity of the reference model itself: max |ddG_gpu - ddG_cpu_topk| =",
+          float(np.abs(ddg - ref.numpy())[valid].max()))

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(engine.SYMBOLS)
     for s in declared:
         assert hasattr(lib, s), s
-    assert lib.tmpnn_abi_version() == 1
+    assert lib.tmpnn_abi_version() == 2
 
 
 def test_weight_contract_matches_reference_checkpoint():
@@ -110,3 +110,113 @@ def test_bench_reference_arm_prints_one_json_line():
               "e2e", "cpu_baseline"):
         assert k in d, k
     assert d["impl"] == "reference" and d["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+REF = "/root/reference"
+needs_ref = pytest.mark.skipif(not os.path.exists(os.path.join(REF, "models", "thermoMPNN_default.pt")), reason="needs the reference checkout")
+
+
+def test_cfg_weight_contracts():
+    """cfg.model variants (transfer_model.py:58-73): the weight table follows hid_sizes = [128 F + 128] + hidden_dims + [21]."""
+    lib = engine.load_library()
+    t = engine.weight_table(engine.ModelCfg.make(3, False, (48,), True))
+    names = [n for n, *_ in t]
+    assert "light_attention.feature_convolution.weight_center" not in names
+    shapes = {n: (r, c) for n, _, r, c in t}
+    assert shapes["both_out.1.weight"] == (48, 512) and shapes["both_out.3.weight"] == (21, 48) and "both_out.5.weight" not in shapes
+    t2 = {n: (r, c) for n, _, r, c in engine.weight_table(engine.ModelCfg.make(1, True, (32, 16, 8), True))}
+    assert t2["light_attention.feature_convolution.weight_center"] == (256, 256) and t2["both_out.7.weight"] == (21, 8)
+    t3 = [n for n, *_ in engine.weight_table(engine.ModelCfg.make(has_head=False))]
+    assert t3[-1] == "prot_mpnn.W_out.bias" and all(n.startswith("prot_mpnn.") for n in t3)
+    bad = engine.ModelCfg.make(4, True, (64,), True)
+    assert lib.tmpnn_cfg_weight_count(ctypes.byref(bad)) < 0
+    with pytest.raises(ValueError):
+        engine.weight_table(bad)
+    # the default-cfg forms are the cfg forms at the default cfg
+    d = engine.ModelCfg()
+    lib.tmpnn_default_cfg(ctypes.byref(d))
+    assert d.key() == engine.ModelCfg.make().key() == (2, 1, (64, 32), 1)
+    assert lib.tmpnn_cfg_weight_blob_floats(ctypes.byref(d)) == lib.tmpnn_weight_blob_floats()
+
+
+def test_cfg_variant_fixture_packs():
+    from conftest import cfg_variant
+    from thermompnn_b200.transfer_model import AttrDict, TransferModel, default_config
+    for tag in ("v1", "v2", "v3"):
+        cfgd, w, _ = cfg_variant(tag)
+        cfg = default_config()
+        cfg.model.update(cfgd)
+        m = TransferModel(cfg, state=w)
+        assert m.weight_blob.numel() == engine.load_library().tmpnn_cfg_weight_blob_floats(ctypes.byref(m._mcfg))
+
+
+@needs_ref
+def test_get_trained_model_paths_like_upstream():
+    """thermompnn_benchmarking.py:78-84: <thermompnn_dir>/<checkpt_dir>/<model_name> unless override_custom; the stock
+    Lightning .pt loads and equals the slim fixture tensor for tensor."""
+    from thermompnn_b200.transfer_model import default_config, get_trained_model
+    cfg = default_config(REF)
+    a = get_trained_model("thermoMPNN_default.pt", cfg)                                  # upstream's default call
+    b = get_trained_model(os.path.join(REF, "models", "thermoMPNN_default.pt"), cfg, override_custom=True)
+    c = get_trained_model(CKPT, override_custom=True)
+    assert (a.weight_blob == b.weight_blob).all() and (a.weight_blob == c.weight_blob).all()
+    with pytest.raises(FileNotFoundError):
+        get_trained_model("thermoMPNN_default.pt", default_config("/nonexistent"))
+    state = load_state(os.path.join(REF, "models", "thermoMPNN_default.pt"))
+    slim = load_state(CKPT)
+    assert set(state) == set(slim) and all(np.array_equal(state[k].reshape(-1), slim[k].reshape(-1)) for k in slim)
+
+
+@needs_ref
+def test_constructors_follow_get_protein_mpnn():
+    """transfer_model.py:17-37: the vanilla checkpoint under <thermompnn_dir>/vanilla_model_weights is required
+    (no silent random weights), any v_48_* version loads into ProteinMPNNBaseline."""
+    import torch
+    from thermompnn_b200.transfer_model import ProteinMPNNBaseline, TransferModel, default_config
+    with pytest.raises(FileNotFoundError):
+        TransferModel(default_config("/nonexistent"))
+    m = TransferModel(default_config(REF))
+    van = torch.load(os.path.join(REF, "vanilla_model_weights", "v_48_020.pt"), map_location="cpu", weights_only=True)["model_state_dict"]
+    tab = {n: (o, r * c) for n, o, r, c in engine.weight_table()}
+    o, n = tab["prot_mpnn.W_e.weight"]
+    assert np.array_equal(m.weight_blob.numpy()[o:o + n], van["W_e.weight"].numpy().reshape(-1))
+    for version in ("v_48_002.pt", "v_48_010.pt", "v_48_030.pt"):
+        b = ProteinMPNNBaseline(default_config(REF), version=version)
+        van = torch.load(os.path.join(REF, "vanilla_model_weights", version), map_location="cpu", weights_only=True)["model_state_dict"]
+        tab = {n: (o, r * c) for n, o, r, c in engine.weight_table(b._mcfg)}
+        o, n = tab["prot_mpnn.W_out.weight"]
+        assert np.array_equal(b.weight_blob.numpy()[o:o + n], van["W_out.weight"].numpy().reshape(-1))
+
+
+def test_positions_follow_tensor_indexing():
+    from thermompnn_b200.transfer_model import TransferModel
+    muts = [Mutation(-1, "A", "C"), None, Mutation(3, "A", "C"), Mutation(-10, "A", "C")]
+    idx, pos = TransferModel._positions(muts, 10)
+    assert idx == [0, 2, 3] and pos.tolist() == [9, 3, 0]
+    for bad in (10, -11):
+        with pytest.raises(IndexError, match="out of bounds"):
+            TransferModel._positions([Mutation(bad, "A", "C")], 10)
+
+
+def test_engine_run_validates_host_buffers():
+    """Arguments that reach C as raw pointers are checked first (no GPU needed: the checks come before the call)."""
+    class Dummy(engine.Engine):
+        def __init__(self): self._lib = None; self._ctx = None
+        def __del__(self): pass
+    e = Dummy()
+    p = featurize_batch([synth(10, 1)])
+    args = (p.offsets, p.X, p.S, p.residue_idx, p.chain_enc, p.mask)
+    with pytest.raises(ValueError, match="float32"):
+        e.run(*args, out=np.empty((10, 21), np.float64))
+    with pytest.raises(ValueError, match="10 x 21"):
+        e.run(*args, out=np.empty((9, 21), np.float32))
+    with pytest.raises(ValueError, match="C-contiguous"):
+        e.run(*args, out=np.empty((21, 10), np.float32).T)
+    with pytest.raises(ValueError, match="log_probs"):
+        e.run(*args, log_probs=np.empty((10, 20), np.float32))
+    with pytest.raises(ValueError, match="raw device pointers"):
+        e.run(*args, out=123, flags=engine.IN_DEVICE | engine.OUT_DEVICE)
+    with pytest.raises(ValueError, match="nothing to compute"):
+        e.run(*args, want_table=False)
+    with pytest.raises(ValueError, match="sizes do not match"):
+        e.run(p.offsets, p.X[:5], p.S, p.residue_idx, p.chain_enc, p.mask)

@@ -76,3 +76,55 @@ def test_fp64_oracle_brackets_fp32_noise(oracle_weights):
     w64 = O.cast_weights(oracle_weights, torch.float64)
     _, ddg64, _ = O.ssm_table(w64, pdb, dtype=torch.float64)
     assert np.nanmax(np.abs(ddg64.numpy() - d["ddG"])) <= 5e-5
+
+
+# ---- round-2 fixtures (tools/make_golden_r2.py, also made by the unmodified reference) -----------------------------
+@pytest.mark.parametrize("name", ["synth600", "synth2000"])
+def test_oracle_long_proteins(name, oracle_weights):
+    """L > 512 (the CUDA k-NN kernel's shared-memory row path) and BASELINE configs[4]'s protein length."""
+    d, pdb = load_case(name)
+    tr = {}
+    _, ddg, _ = O.ssm_table(oracle_weights, pdb, trace=tr)
+    assert np.array_equal(tr["E_idx"].numpy(), d["E_idx"])
+    assert np.abs(ddg.numpy() - d["ddG"]).max() <= 5e-6
+    assert np.abs(tr["log_probs"].numpy() - d["log_probs"]).max() <= 2e-5
+
+
+def test_oracle_log_probs(oracle_weights):
+    """ProteinMPNN's own output layer (protein_mpnn_utils.py:1275-1277) on the round-1 cases."""
+    lp = np.load(os.path.join(GOLDEN, "extra_logprobs.npz"))
+    for name in lp.files:
+        _, pdb = load_case(name)
+        tr = {}
+        O.ssm_table(oracle_weights, pdb, trace=tr)
+        got = tr["log_probs"].numpy()
+        assert np.abs(got - lp[name]).max() <= 2e-5, name
+        assert np.abs(np.exp(got).sum(-1) - 1).max() <= 1e-5
+
+
+def test_oracle_c4_batch(oracle_weights):
+    """Megascale-shaped proteins (L 32..72, half of them K = L < 48; BASELINE configs[3])."""
+    from conftest import c4_batch
+    d, pdbs = c4_batch()
+    o = 0
+    for pdb in pdbs[::6]:
+        i = [p["name"] for p in pdbs].index(pdb["name"])
+        o = int(d["lengths"][:i].sum())
+        _, ddg, _ = O.ssm_table(oracle_weights, pdb)
+        assert np.abs(ddg.numpy() - d["ddG"][o:o + len(pdb["seq"])]).max() <= 5e-6, pdb["name"]
+
+
+def test_oracle_cfg_variants(oracle_weights):
+    """Other cfg.model heads (transfer_model.py:45-73): 3 final layers without LightAttention, 1 final layer with it, none."""
+    from conftest import cfg_variant
+    for tag in ("v1", "v2", "v3"):
+        cfg, w, ddgs = cfg_variant(tag, oracle_weights)
+        for pn, ref in ddgs.items():
+            pdb = synth_by_name(pn)
+            _, ddg, _ = O.ssm_table(w, pdb, num_final_layers=cfg["num_final_layers"], lightattn=cfg["lightattn"])
+            assert np.abs(ddg.numpy() - ref).max() <= 5e-6, (tag, pn)
+
+
+def synth_by_name(pn):
+    from thermompnn_b200.synth import synth
+    return {"synth90": synth(90, seed=90), "synth40": synth(40, seed=7)}[pn]

@@ -56,3 +56,64 @@ def test_csv_frame_matches_published_layout():
     assert pdb_id == "2OCJ" and list(df.columns) == list(ref.columns) and len(df) == len(ref) == 3880
     for col in ("Model", "Dataset", "position", "wildtype", "mutation", "pdb", "chain"):
         assert (df[col].astype(str).values == ref[col].astype(str).values).all(), col
+
+
+REF = "/root/reference"
+
+
+def _random_pdb(path, rng):
+    """PDB text with the quirks the reference parser has rules for: several chains, numbering gaps, insertion codes,
+    negative residue numbers, MSE HETATMs, unknown residues, missing atoms, duplicated (alt-loc) atoms, side chains."""
+    aa3 = ["ALA", "ARG", "ASN", "ASP", "CYS", "GLN", "GLU", "GLY", "HIS", "ILE", "LEU", "LYS", "MET", "PHE", "PRO", "SER",
+           "THR", "TRP", "TYR", "VAL", "UNK", "MSE"]
+    lines, serial = ["HEADER    TEST", "REMARK 1"], 1
+    for ch in rng.permutation(list("ABcd1"))[:int(rng.integers(1, 5))]:
+        num = int(rng.integers(-3, 20))
+        for _ in range(int(rng.integers(3, 60))):
+            num += 1 if rng.random() > 0.1 else int(rng.integers(2, 5))
+            for ins in ([" "] + (["A", "B"][:int(rng.integers(1, 3))] if rng.random() < 0.08 else [])):
+                res = aa3[int(rng.integers(0, len(aa3)))]
+                rec = "HETATM" if res == "MSE" else "ATOM"
+                for name in ("N", "CA", "C", "O", "CB"):
+                    if name != "CB" and rng.random() < 0.03:
+                        continue
+                    for _rep in range(2 if rng.random() < 0.05 else 1):
+                        x, y, z = rng.normal(scale=30, size=3)
+                        lines.append(f"{rec:<6}{serial:>5} {name:<4} {res:>3} {ch}{num:>4}{ins:1}   {x:8.3f}{y:8.3f}{z:8.3f}  1.00  0.00")
+                        serial += 1
+        lines.append("TER")
+    open(path, "w").write("\n".join(lines) + "\nEND\n")
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "protein_mpnn_utils.py")), reason="needs the reference checkout")
+def test_parser_differential_against_live_reference(tmp_path):
+    """Random PDB text through the reference's own parsers and ours: every key, every float64, resn_list included
+    (also with the default chain list, where upstream ends on list('no_chain'))."""
+    import sys
+    sys.path.insert(0, REF)
+    import protein_mpnn_utils as R
+    from thermompnn_b200.pdb import parse_PDB
+    rng = np.random.default_rng(5)
+    for it in range(12):
+        p = str(tmp_path / f"rand{it}.pdb")
+        _random_pdb(p, rng)
+        for chains in (None, "A", "AB", ["c", "1", "Z"], "ZA"):
+            for ours, theirs in ((alt_parse_PDB(p, chains), R.alt_parse_PDB(p, chains)), (parse_PDB(p, chains), R.parse_PDB(p, chains))):
+                assert len(ours) == len(theirs) == 1
+                a, b = ours[0], theirs[0]
+                assert list(a.keys()) == list(b.keys()), (chains, list(a.keys()), list(b.keys()))
+                for k in b:
+                    if k.startswith("coords_chain_"):
+                        for kk in b[k]:
+                            assert np.array_equal(np.asarray(a[k][kk], dtype=np.float64), np.asarray(b[k][kk], dtype=np.float64), equal_nan=True), (k, kk)
+                    else:
+                        assert a[k] == b[k], (chains, k, a[k], b[k])
+
+
+def test_parser_resn_list_semantics():
+    """resn_list is what the LAST chain letter iterated produced (protein_mpnn_utils.py:346)."""
+    p = os.path.join(GOLDEN, "2OCJ.pdb")
+    assert alt_parse_PDB(p)[0]["resn_list"] == list("no_chain")           # default chain list ends on letters not in the file
+    assert alt_parse_PDB(p, "BZ")[0]["resn_list"] == list("no_chain")
+    a = alt_parse_PDB(p, "A")[0]["resn_list"]
+    assert alt_parse_PDB(p, "BA")[0]["resn_list"] == a and a[0] == "96" and len(a) == 194

@@ -35,12 +35,25 @@ struct PendingEvent {
     cudaEvent_t a, b;
 };
 
+uint64_t g_realloc_count = 0;   // (per process; only ever compared for equality)
+
+struct DeviceGuard {   // the C ABI must not change the caller's current device (a torch process may be on another GPU)
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
     size_t cap = 0;
     cudaError_t reserve(size_t n) {
         if (n <= cap) return cudaSuccess;
+        ++g_realloc_count;
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
@@ -54,12 +67,24 @@ struct DevBuf {
 
 }  // namespace
 
+struct GraphKey {   // everything a captured kernel chain depends on besides the staged input bytes
+    int B = -1, N = 0, lmax = 0, stop = 0;
+    uint32_t flags = 0;
+    const void* ptr[7] = {};
+    uint64_t epoch = 0;
+    bool operator==(const GraphKey& o) const {
+        return B == o.B && N == o.N && lmax == o.lmax && stop == o.stop && flags == o.flags && epoch == o.epoch &&
+               std::memcmp(ptr, o.ptr, sizeof(ptr)) == 0;
+    }
+};
+
 struct tmpnn_ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     std::string err;
 
+    tmpnn_model_cfg cfg = default_model_cfg();
     std::vector<RawTensor> raw;
     DevLayout lay{};
     float* d_weights = nullptr;
@@ -72,18 +97,37 @@ struct tmpnn_ctx {
     cudaEvent_t stage_ev = nullptr;   // completion of the last H2D out of h_stage
     bool stage_busy = false;
     // per-node
-    DevBuf<float> atoms, maskf, hV, dec_prev, dec_last, Ssum, cnt, P, Q, P2, Q2, table, Spart;
+    DevBuf<float> atoms, maskf, hV, dec_first, dec_prev, dec_last, P, Q, P2, Q2, table, logp, Spart;
+    DevBuf<int> S_dev;                // S clamped to 0..20 by the first kernel
     // per-edge
     DevBuf<int> E_idx;
     DevBuf<float> D_nb, hE;
+    uint64_t buf_epoch = 0;           // bumped whenever a buffer above is reallocated (invalidates the captured graph)
+
+    int* d_err = nullptr;             // sticky device flag: bit 0 = a letter outside 0..20 was clamped
+    int* h_err = nullptr;             // pinned mirror, refreshed at the end of every run
+    bool clear_err = false;
+    cudaEvent_t run_ev = nullptr;     // completion of the last run (orders runs on different streams, fetch)
+    bool run_pending = false;
 
     int last_N = 0;
     float* last_table = nullptr;
+    float* last_logp = nullptr;
     int debug_stop = 0;
-    // tensor-core edge kernels; TMPNN_TC=<mask> (bring-up / error localisation only): bit 0 edge_feat, 1 msg, 2 edge_upd;
-    // 0 selects the FP32 SIMT generation everywhere
+
+    // replay: the kernel chain of the last call shape, captured once it repeats
+    bool graphs = true;
+    GraphKey last_key, graph_key;
+    cudaGraphExec_t graph_exec = nullptr;
+    int64_t graph_launches = 0, graph_kernels = 0;
+
+#ifdef TMPNN_DEV
+    DevBuf<float> Ssum, cnt;          // SIMT message kernels' outputs
+    // TMPNN_TC=<mask> (bring-up / error localisation only): bit 0 edge_feat, 1 msg, 2 edge_upd; 0 selects the FP32 SIMT
+    // generation everywhere
     int tc_mask = 7;
-    long long* d_trace = nullptr;   // TMPNN_TC_TRACE=1: phase stamps of enc layer 1's message and edge-update kernels (dev tool)
+#endif
+    long long* d_trace = nullptr;     // -DTMPNN_DEV + TMPNN_TC_TRACE=1: phase stamps of enc layer 1's kernels
 
     bool profiling = false;
     std::vector<ProfEntry> prof;
@@ -126,6 +170,7 @@ struct Prep {
         dev.resize(dev.size() + padded, 0.f);
         return off;
     }
+#ifdef TMPNN_DEV
     // KN[k][n] = W[n][col0 + k] for a row-major nn.Linear weight W[out][in]
     void put_kn(int64_t off, const std::string& name, int col0, int ncols) {
         int out, in;
@@ -133,14 +178,7 @@ struct Prep {
         for (int k = 0; k < ncols; ++k)
             for (int n = 0; n < out; ++n) dev[off + (int64_t)k * out + n] = W[(int64_t)n * in + col0 + k];
     }
-    int64_t kn(const std::string& name, int col0 = 0, int ncols = -1) {
-        int out, in;
-        find(name, &out, &in);
-        if (ncols < 0) ncols = in;
-        int64_t off = alloc((int64_t)ncols * out);
-        put_kn(off, name, col0, ncols);
-        return off;
-    }
+#endif
     int64_t vec(const std::string& name) {
         int r, c;
         const float* v = find(name, &r, &c);
@@ -209,20 +247,9 @@ struct Prep {
                     dev[idx + 4096] = lo;
                 }
     }
-    // KN of an nn.Linear [out][in] padded to 128 output columns, appended at off; returns floats written
-    int64_t put_kn_padded(int64_t off, const std::string& name, int col0, int ncols_out_begin, int k_rows) {
-        int out, in;
-        const float* W = find(name, &out, &in);
-        for (int k = 0; k < k_rows; ++k)
-            for (int n = 0; n < HID; ++n) {
-                int oc = ncols_out_begin + n;
-                dev[off + (int64_t)k * HID + n] = (oc < out && col0 + k < in) ? W[(int64_t)oc * in + col0 + k] : 0.f;
-            }
-        return (int64_t)k_rows * HID;
-    }
 };
 
-DevLayout prepare_weights(Prep& P) {
+DevLayout prepare_weights(Prep& P, const tmpnn_model_cfg& cfg) {
     DevLayout L{};
     const std::string pm = "prot_mpnn.";
     {   // positional table: Linear(one_hot(q)) = W[:, q] + b   (protein_mpnn_utils.py:906-907)
@@ -232,9 +259,11 @@ DevLayout prepare_weights(Prep& P) {
         for (int q = 0; q < 66; ++q)
             for (int t = 0; t < 16; ++t) P.dev[L.pos_table + q * 16 + t] = W[t * 66 + q] + b[t];
     }
+#ifdef TMPNN_DEV
     L.feat = P.alloc((int64_t)(EDGE_IN + HID) * HID);
     P.put_kn(L.feat, pm + "features.edge_embedding.weight", 0, EDGE_IN);
     P.put_kn(L.feat + (int64_t)EDGE_IN * HID, pm + "W_e.weight", 0, HID);
+#endif
     L.tc_feat = P.alloc(17 * 8192);
     P.put_tc(L.tc_feat, pm + "features.edge_embedding.weight", 0, 13);
     P.put_tc(L.tc_feat + 13 * 8192, pm + "W_e.weight", 0, 4);
@@ -250,18 +279,20 @@ DevLayout prepare_weights(Prep& P) {
     for (int l = 0; l < 3; ++l) {
         const std::string p = pm + "encoder_layers." + std::to_string(l) + ".";
         EncW& e = L.enc[l];
+#ifdef TMPNN_DEV
         e.msg = P.alloc(2 * HID * HID);
         P.put_kn(e.msg, p + "W1.weight", HID, HID);
         P.put_kn(e.msg + HID * HID, p + "W2.weight", 0, HID);
+        e.edge = P.alloc(3 * HID * HID);
+        P.put_kn(e.edge, p + "W11.weight", HID, HID);
+        P.put_kn(e.edge + HID * HID, p + "W12.weight", 0, HID);
+        P.put_kn(e.edge + 2 * HID * HID, p + "W13.weight", 0, HID);
+#endif
         e.tc_msg = P.alloc(8 * 8192);
         P.put_tc(e.tc_msg, p + "W1.weight", HID);
         P.put_tc(e.tc_msg + 4 * 8192, p + "W2.weight", 0);
         e.b1 = P.vec(p + "W1.bias");
         e.b2 = P.vec(p + "W2.bias");
-        e.edge = P.alloc(3 * HID * HID);
-        P.put_kn(e.edge, p + "W11.weight", HID, HID);
-        P.put_kn(e.edge + HID * HID, p + "W12.weight", 0, HID);
-        P.put_kn(e.edge + 2 * HID * HID, p + "W13.weight", 0, HID);
         e.tc_edge = P.alloc(12 * 8192);
         P.put_tc(e.tc_edge, p + "W11.weight", HID);
         P.put_tc(e.tc_edge + 4 * 8192, p + "W12.weight", 0);
@@ -288,9 +319,11 @@ DevLayout prepare_weights(Prep& P) {
     for (int l = 0; l < 3; ++l) {
         const std::string p = pm + "decoder_layers." + std::to_string(l) + ".";
         DecW& d = L.dec[l];
+#ifdef TMPNN_DEV
         d.msg = P.alloc(2 * HID * HID);
         P.put_kn(d.msg, p + "W1.weight", HID, HID);
         P.put_kn(d.msg + HID * HID, p + "W2.weight", 0, HID);
+#endif
         d.tc_msg = P.alloc(8 * 8192);
         P.put_tc(d.tc_msg, p + "W1.weight", HID);
         P.put_tc(d.tc_msg + 4 * 8192, p + "W2.weight", 0);
@@ -315,7 +348,10 @@ DevLayout prepare_weights(Prep& P) {
         }
     }
     L.Ws = P.vec(pm + "W_s.weight");
-    {   // head weights in step order (14 steps, all K-split: group q = rows (q*steps + s)*32.. of the phase's matrix)
+    L.Wout = P.vec(pm + "W_out.weight");
+    L.bout = P.vec(pm + "W_out.bias");
+    if (cfg.has_head && cfg_is_default(cfg)) {
+        // head weights in step order (14 steps, all K-split: group q = rows (q*steps + s)*32.. of the phase's matrix)
         L.head = P.alloc((int64_t)56 * 4096);
         int64_t o = L.head;
         for (int blk = 0; blk < 3; ++blk)
@@ -326,14 +362,31 @@ DevLayout prepare_weights(Prep& P) {
             for (int q = 0; q < 4; ++q) o += P.put_chunk(o, "both_out.1.weight", 0, (3 * q + s) * 32);
         for (int q = 0; q < 4; ++q) o += P.put_chunk(o, "both_out.3.weight", 0, 32 * q);
         for (int q = 0; q < 4; ++q) o += P.put_chunk(o, "both_out.5.weight", 0, 32 * q);
+        L.la_b = P.vec("light_attention.feature_convolution.bias");
+        L.m1_b = P.vec("both_out.1.bias");
+        L.m2_b = P.vec("both_out.3.bias");
+        L.m3_b = P.vec("both_out.5.bias");
     }
-    L.la_b = P.vec("light_attention.feature_convolution.bias");
-    L.m1_b = P.vec("both_out.1.bias");
-    L.m2_b = P.vec("both_out.3.bias");
-    L.m3_b = P.vec("both_out.5.bias");
-    L.ddg = P.alloc(2);
-    P.dev[L.ddg] = *P.find("ddg_out.weight");
-    P.dev[L.ddg + 1] = *P.find("ddg_out.bias");
+    if (cfg.has_head) {
+        // the same matrices as nn.Linear stores them, for the generic head kernel (any cfg)
+        int n = 0;
+        auto add_layer = [&](const std::string& w, const std::string& b) {
+            int r, c;
+            P.find(w, &r, &c);
+            L.gen_in[n] = c; L.gen_out[n] = r;
+            L.gen_w[n] = P.vec(w); L.gen_b[n] = P.vec(b);
+            ++n;
+        };
+        if (cfg.lightattn) add_layer("light_attention.feature_convolution.weight_center", "light_attention.feature_convolution.bias");
+        for (int i = 0; i <= cfg.n_hidden; ++i) {
+            const std::string q = "both_out." + std::to_string(2 * i + 1);
+            add_layer(q + ".weight", q + ".bias");
+        }
+        L.gen_layers = n;
+        L.ddg = P.alloc(2);
+        P.dev[L.ddg] = *P.find("ddg_out.weight");
+        P.dev[L.ddg + 1] = *P.find("ddg_out.bias");
+    }
     L.zeros = P.alloc(HID);
     L.total = (int64_t)P.dev.size();
     return L;
@@ -395,7 +448,8 @@ void drain_profile(tmpnn_ctx* c) {
 
 size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-// Residues per tile: minimise (waves over the SMs) x (tile size), preferring big tiles when the grid is deep.
+#ifdef TMPNN_DEV
+// Residues per tile of the SIMT edge kernels: minimise (waves over the SMs) x (tile size).
 int choose_npt(int N, int sms) {
     int best = 4;
     double best_cost = 1e30;
@@ -411,6 +465,217 @@ int choose_npt(int N, int sms) {
     if (N >= 16 * sms) best = 4;
     return best;
 }
+#endif
+
+const std::vector<RawTensor>& raw_table_default() {
+    static const std::vector<RawTensor> t = build_raw_table(default_model_cfg());
+    return t;
+}
+// The table of the cfg last asked about (name pointers handed out by tmpnn_cfg_weight_info stay valid until the next
+// call with a different cfg on this thread).
+const std::vector<RawTensor>& raw_table_for(const tmpnn_model_cfg& cfg) {
+    if (cfg_is_default(cfg)) return raw_table_default();
+    static thread_local tmpnn_model_cfg cached{};
+    static thread_local std::vector<RawTensor> t;
+    if (t.empty() || std::memcmp(&cached, &cfg, sizeof(cfg)) != 0) {
+        t = build_raw_table(cfg);
+        cached = cfg;
+    }
+    return t;
+}
+int64_t table_floats(const std::vector<RawTensor>& t) { return t.back().offset + (int64_t)t.back().rows * t.back().cols; }
+
+void drop_graph(tmpnn_ctx* c) {
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    c->graph_exec = nullptr;
+    c->graph_key = GraphKey{};
+}
+
+// A letter outside 0..20 reached the device (TMPNN_IN_DEVICE callers): reported once, then the flag is cleared.
+int take_range_error(tmpnn_ctx* c) {
+    if (c->h_err && *c->h_err) {
+        *c->h_err = 0;
+        c->clear_err = true;
+        return fail(c, TMPNN_E_RANGE, "tmpnn_run_batch: a device-side S value outside 0..20 was clamped to 20 ('X')");
+    }
+    return TMPNN_OK;
+}
+
+// Device addresses of one call's inputs / outputs.
+struct RunIO {
+    const int* off; const float* X; const int* S; const int* r; const int* c; const uint8_t* m;
+    float* table; float* logp;          // device destinations (either may be NULL = not wanted)
+    float* host_table; float* host_logp;   // host destinations of the D2H copies, or NULL
+    size_t stage_bytes;
+    int B, N, lmax;
+};
+
+// Enqueue the kernel chain of a call and the D2H of its results on `st` (the staged inputs are already on their way).
+// Used both directly and under stream capture (so nothing here may synchronise, allocate or record a host-visible event).
+int enqueue_pipeline(tmpnn_ctx* ctx, const RunIO& io, cudaStream_t st) {
+    const int N = io.N, B = io.B;
+    const size_t n = (size_t)N;
+    const float* W = ctx->d_weights;
+    const DevLayout& L = ctx->lay;
+    const int stop = ctx->debug_stop;
+    bool done = false;
+    auto stage_done = [&](int s) { if (stop == s) done = true; return done; };
+    const int* d_S = ctx->S_dev.p;
+#ifdef TMPNN_DEV
+    const int npt = choose_npt(N, ctx->sm_count);
+    const int tc_mask = ctx->tc_mask;
+#else
+    constexpr int tc_mask = 7;
+#endif
+
+    // (h_V starts at zero, protein_mpnn_utils.py:1225; cleared up front so that no memset sits between two kernels
+    // of the programmatic-dependent-launch chain)
+    CU(cudaMemsetAsync(ctx->hV.p, 0, n * HID * sizeof(float), st));
+    { LaunchScope ls(ctx, st, "knn");
+      launch_knn(io.off, B, io.X, io.m, io.S, N, io.lmax, ctx->atoms.p, ctx->maskf.p, ctx->S_dev.p, ctx->d_err, ctx->E_idx.p,
+                 ctx->D_nb.p, st); }
+    if (!stage_done(1)) {
+        if (tc_mask & 1) {
+            LaunchScope ls(ctx, st, "tc_edge_feat");
+            launch_tc_edge_feat(ctx->atoms.p, ctx->E_idx.p, ctx->D_nb.p, io.r, io.c, W + L.pos_table, W + L.rbf_mu, W + L.tc_feat,
+                                W + L.ne.g, W + L.ne.b, W + L.be, ctx->hE.p, N, ctx->sm_count, st);
+        }
+#ifdef TMPNN_DEV
+        else {
+            LaunchScope ls(ctx, st, "edge_feat");
+            launch_edge_feat(npt, ctx->atoms.p, ctx->E_idx.p, ctx->D_nb.p, io.r, io.c, W + L.pos_table, W + L.rbf_mu,
+                             W + L.feat, W + L.ne.g, W + L.ne.b, W + L.be, ctx->hE.p, N, st);
+        }
+#endif
+    }
+    if (!done && !stage_done(2)) {
+        for (int l = 0; l < 3 && !done; ++l) {
+            const EncW& e = L.enc[l];
+            {   // first layer: h_V = 0, so P_i = b1 and Q_j = 0 (one shared row each, stride 0)
+                const float* Pp = l == 0 ? W + e.b1 : ctx->P.p;
+                const float* Qp = l == 0 ? W + L.zeros : ctx->Q.p;
+                const int stride = l == 0 ? 0 : HID;
+                if (tc_mask & 2) {
+                    LaunchScope ls(ctx, st, "tc_enc_msg");
+                    launch_tc_msg(false, ctx->hE.p, ctx->E_idx.p, Pp, stride, Qp, stride, ctx->maskf.p, W + e.tc_msg, W + e.b2,
+                                  ctx->Spart.p, N, ctx->sm_count, st, l == 1 ? ctx->d_trace : nullptr);
+                }
+#ifdef TMPNN_DEV
+                else {
+                    LaunchScope ls(ctx, st, "enc_msg");
+                    launch_msg(npt, false, ctx->hE.p, ctx->E_idx.p, Pp, stride, Qp, stride, ctx->maskf.p, W + e.msg, W + e.b2,
+                               ctx->Ssum.p, ctx->cnt.p, N, st);
+                }
+#endif
+            }
+            NodeUpdArgs a{};
+            a.weights = W; a.w = e.nu; a.hV = ctx->hV.p; a.hV_copy = nullptr;
+            a.Spart = ctx->Spart.p; a.E_idx = ctx->E_idx.p; a.enc = 1;
+#ifdef TMPNN_DEV
+            a.Ssum = ctx->Ssum.p; a.cnt = ctx->cnt.p;
+            if (!(tc_mask & 2)) a.Spart = nullptr;
+#endif
+            a.maskf = ctx->maskf.p; a.S = d_S; a.N = N;
+            a.trace = (l == 1 && ctx->d_trace) ? ctx->d_trace + 1024 : nullptr;
+            a.proj[0] = {e.b11, -1, ctx->P2.p};     // edge update of this layer
+            a.proj[1] = {-1, -1, ctx->Q2.p};
+            if (l < 2) {
+                const EncW& nx = L.enc[l + 1];
+                a.proj[2] = {nx.b1, -1, ctx->P.p};
+                a.proj[3] = {-1, -1, ctx->Q.p};
+            } else {
+                const DecW& nx = L.dec[0];
+                a.proj[2] = {nx.b1, -1, ctx->P.p};
+                a.proj[3] = {-1, nx.Tseq, ctx->Q.p};
+            }
+            a.nproj = 4;
+            { LaunchScope ls(ctx, st, "node_update"); launch_node_update(a, ctx->sm_count, st); }
+            if (tc_mask & 4) {
+                LaunchScope ls(ctx, st, "tc_edge_upd");
+                launch_tc_edge_upd(ctx->hE.p, ctx->E_idx.p, ctx->P2.p, ctx->Q2.p, ctx->maskf.p, W + e.tc_edge, W + e.b12, W + e.b13,
+                                   W + e.n3.g, W + e.n3.b, N, ctx->sm_count, st, (l == 1 && ctx->d_trace) ? ctx->d_trace + 512 : nullptr);
+            }
+#ifdef TMPNN_DEV
+            else {
+                LaunchScope ls(ctx, st, "edge_upd");
+                launch_edge_upd(npt, ctx->hE.p, ctx->E_idx.p, ctx->P2.p, ctx->Q2.p, W + e.edge, W + e.b12, W + e.b13,
+                                W + e.n3.g, W + e.n3.b, N, st);
+            }
+#endif
+            stage_done(3 + l);
+        }
+    }
+    if (!done) {
+        for (int l = 0; l < 3 && !done; ++l) {
+            const DecW& d = L.dec[l];
+            if (tc_mask & 2) {
+                LaunchScope ls(ctx, st, "tc_dec_msg");
+                launch_tc_msg(true, ctx->hE.p, ctx->E_idx.p, ctx->P.p, HID, ctx->Q.p, HID, ctx->maskf.p, W + d.tc_msg, W + d.b2,
+                              ctx->Spart.p, N, ctx->sm_count, st);
+            }
+#ifdef TMPNN_DEV
+            else {
+                LaunchScope ls(ctx, st, "dec_msg");
+                launch_msg(npt, true, ctx->hE.p, ctx->E_idx.p, ctx->P.p, HID, ctx->Q.p, HID, ctx->maskf.p, W + d.msg,
+                           W + d.b2, ctx->Ssum.p, ctx->cnt.p, N, st);
+            }
+#endif
+            NodeUpdArgs a{};
+            a.weights = W; a.w = d.nu; a.hV = ctx->hV.p;
+            a.Spart = ctx->Spart.p; a.E_idx = ctx->E_idx.p; a.enc = 0;
+#ifdef TMPNN_DEV
+            a.Ssum = ctx->Ssum.p; a.cnt = ctx->cnt.p;
+            if (!(tc_mask & 2)) a.Spart = nullptr;
+#endif
+            a.hV_copy = l == 0 ? ctx->dec_first.p : (l == 1 ? ctx->dec_prev.p : ctx->dec_last.p);
+            a.maskf = ctx->maskf.p; a.S = d_S; a.N = N;
+            a.nproj = 0;
+            if (l < 2) {
+                const DecW& nx = L.dec[l + 1];
+                a.proj[0] = {nx.b1, -1, ctx->P.p};
+                a.proj[1] = {-1, nx.Tseq, ctx->Q.p};
+                a.nproj = 2;
+            }
+            { LaunchScope ls(ctx, st, "node_update"); launch_node_update(a, ctx->sm_count, st); }
+            stage_done(6 + l);
+        }
+    }
+    if (!done) {
+        if (io.table) {
+            if (cfg_is_default(ctx->cfg)) {
+                HeadArgs h{};
+                h.weights = W; h.stream = L.head; h.Ws = L.Ws; h.la_b = L.la_b; h.m1_b = L.m1_b; h.m2_b = L.m2_b;
+                h.m3_b = L.m3_b; h.ddg = L.ddg;
+                h.dec_last = ctx->dec_last.p; h.dec_prev = ctx->dec_prev.p; h.S = d_S; h.table = io.table; h.N = N;
+                LaunchScope ls(ctx, st, "head");
+                launch_head(h, ctx->sm_count, st);
+            } else {
+                HeadGenArgs h{};
+                h.weights = W; h.nlayers = L.gen_layers; h.relu_first = ctx->cfg.lightattn ? 0 : 1;
+                for (int i = 0; i < L.gen_layers; ++i) {
+                    h.in_dim[i] = L.gen_in[i]; h.out_dim[i] = L.gen_out[i]; h.w[i] = L.gen_w[i]; h.b[i] = L.gen_b[i];
+                }
+                h.Ws = L.Ws; h.ddg = L.ddg;
+                h.dec[0] = ctx->dec_last.p; h.dec[1] = ctx->dec_prev.p; h.dec[2] = ctx->dec_first.p;
+                h.num_final = ctx->cfg.num_final_layers; h.S = d_S; h.table = io.table; h.N = N;
+                LaunchScope ls(ctx, st, "head_generic");
+                launch_head_generic(h, st);
+            }
+        }
+        if (io.logp) {
+            LogProbArgs a{};
+            a.weights = W; a.Wout = L.Wout; a.bout = L.bout; a.hV = ctx->dec_last.p; a.out = io.logp; a.N = N;
+            LaunchScope ls(ctx, st, "log_probs");
+            launch_log_probs(a, st);
+        }
+        if (io.host_table) CU(cudaMemcpyAsync(io.host_table, io.table, n * 21 * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (io.host_logp) CU(cudaMemcpyAsync(io.host_logp, io.logp, n * 21 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaGetLastError());
+    CU(tc_take_error());
+    return TMPNN_OK;
+}
 
 }  // namespace
 
@@ -421,15 +686,16 @@ extern "C" {
 
 int tmpnn_abi_version(void) { return TMPNN_ABI_VERSION; }
 
-static const std::vector<RawTensor>& raw_table() {
-    static const std::vector<RawTensor> t = build_raw_table();
-    return t;
+void tmpnn_default_cfg(tmpnn_model_cfg* cfg) { if (cfg) *cfg = default_model_cfg(); }
+
+int tmpnn_cfg_weight_count(const tmpnn_model_cfg* cfg) {
+    if (!cfg || !cfg_valid(*cfg)) return TMPNN_E_INVALID;
+    return (int)raw_table_for(*cfg).size();
 }
 
-int tmpnn_weight_count(void) { return (int)raw_table().size(); }
-
-int tmpnn_weight_info(int index, const char** name, int64_t* offset, int32_t* rows, int32_t* cols) {
-    const auto& t = raw_table();
+int tmpnn_cfg_weight_info(const tmpnn_model_cfg* cfg, int index, const char** name, int64_t* offset, int32_t* rows, int32_t* cols) {
+    if (!cfg || !cfg_valid(*cfg)) return TMPNN_E_INVALID;
+    const auto& t = raw_table_for(*cfg);
     if (index < 0 || index >= (int)t.size()) return TMPNN_E_INVALID;
     if (name) *name = t[index].name.c_str();
     if (offset) *offset = t[index].offset;
@@ -438,10 +704,19 @@ int tmpnn_weight_info(int index, const char** name, int64_t* offset, int32_t* ro
     return TMPNN_OK;
 }
 
-int64_t tmpnn_weight_blob_floats(void) {
-    const auto& t = raw_table();
-    return t.back().offset + (int64_t)t.back().rows * t.back().cols;
+int64_t tmpnn_cfg_weight_blob_floats(const tmpnn_model_cfg* cfg) {
+    if (!cfg || !cfg_valid(*cfg)) return TMPNN_E_INVALID;
+    return table_floats(raw_table_for(*cfg));
 }
+
+int tmpnn_weight_count(void) { return (int)raw_table_default().size(); }
+
+int tmpnn_weight_info(int index, const char** name, int64_t* offset, int32_t* rows, int32_t* cols) {
+    const tmpnn_model_cfg c = default_model_cfg();
+    return tmpnn_cfg_weight_info(&c, index, name, offset, rows, cols);
+}
+
+int64_t tmpnn_weight_blob_floats(void) { return table_floats(raw_table_default()); }
 
 int tmpnn_create(int device, tmpnn_ctx** out) {
     if (!out) {
@@ -460,15 +735,15 @@ int tmpnn_create(int device, tmpnn_ctx** out) {
         g_create_error = "tmpnn_create: device index out of range";
         return TMPNN_E_INVALID;
     }
+    DeviceGuard guard(device);
     tmpnn_ctx* ctx = new tmpnn_ctx();
     ctx->device = device;
-    ctx->raw = raw_table();
+    ctx->raw = raw_table_default();
     auto bail = [&](const std::string& m) {
         g_create_error = m;
-        delete ctx;
+        tmpnn_destroy(ctx);
         return TMPNN_E_CUDA;
     };
-    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(std::string("cudaSetDevice: ") + cudaGetErrorString(e));
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
         return bail(std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
@@ -478,64 +753,101 @@ int tmpnn_create(int device, tmpnn_ctx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess)
         return bail(std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+    if ((e = cudaEventCreateWithFlags(&ctx->stage_ev, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->run_ev, cudaEventDisableTiming)) != cudaSuccess)
+        return bail(std::string("cudaEventCreate: ") + cudaGetErrorString(e));
+    if ((e = cudaMalloc(&ctx->d_err, sizeof(int))) != cudaSuccess || (e = cudaMemset(ctx->d_err, 0, sizeof(int))) != cudaSuccess ||
+        (e = cudaMallocHost(&ctx->h_err, sizeof(int))) != cudaSuccess)
+        return bail(std::string("error flag allocation: ") + cudaGetErrorString(e));
+    *ctx->h_err = 0;
     if ((e = kernels_init()) != cudaSuccess) return bail(std::string("kernels_init: ") + cudaGetErrorString(e));
     if ((e = node_kernels_init()) != cudaSuccess) return bail(std::string("node_kernels_init: ") + cudaGetErrorString(e));
     if ((e = tc_kernels_init()) != cudaSuccess) return bail(std::string("tc_kernels_init: ") + cudaGetErrorString(e));
+    if ((e = head_kernels_init()) != cudaSuccess) return bail(std::string("head_kernels_init: ") + cudaGetErrorString(e));
+#ifdef TMPNN_DEV
+    if ((e = simt_kernels_init()) != cudaSuccess) return bail(std::string("simt_kernels_init: ") + cudaGetErrorString(e));
     if (const char* env = std::getenv("TMPNN_TC_TRACE"))
         if (std::atoi(env)) { cudaMalloc(&ctx->d_trace, 3 * 512 * sizeof(long long)); cudaMemset(ctx->d_trace, 0, 3 * 512 * sizeof(long long)); }
     if (const char* env = std::getenv("TMPNN_TC")) ctx->tc_mask = std::atoi(env) == 1 ? 7 : std::atoi(env);
+#endif
+    if (const char* env = std::getenv("TMPNN_GRAPHS")) ctx->graphs = std::atoi(env) != 0;
     *out = ctx;
     return TMPNN_OK;
 }
 
 void tmpnn_destroy(tmpnn_ctx* ctx) {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->run_pending && ctx->run_ev) cudaEventSynchronize(ctx->run_ev);
     drain_profile(ctx);
+    drop_graph(ctx);
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->stage_ev) cudaEventDestroy(ctx->stage_ev);
+    if (ctx->run_ev) cudaEventDestroy(ctx->run_ev);
     if (ctx->d_weights) cudaFree(ctx->d_weights);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->d_err) cudaFree(ctx->d_err);
+    if (ctx->h_err) cudaFreeHost(ctx->h_err);
+    if (ctx->d_trace) cudaFree(ctx->d_trace);
     ctx->d_in.release();
-    ctx->atoms.release(); ctx->maskf.release(); ctx->hV.release(); ctx->dec_prev.release(); ctx->dec_last.release();
-    ctx->Ssum.release(); ctx->cnt.release(); ctx->P.release(); ctx->Q.release(); ctx->P2.release(); ctx->Q2.release();
-    ctx->Spart.release();
+    ctx->atoms.release(); ctx->maskf.release(); ctx->hV.release(); ctx->dec_first.release(); ctx->dec_prev.release();
+    ctx->dec_last.release(); ctx->P.release(); ctx->Q.release(); ctx->P2.release(); ctx->Q2.release();
+    ctx->Spart.release(); ctx->S_dev.release(); ctx->logp.release();
     ctx->table.release(); ctx->E_idx.release(); ctx->D_nb.release(); ctx->hE.release();
+#ifdef TMPNN_DEV
+    ctx->Ssum.release(); ctx->cnt.release();
+#endif
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
 const char* tmpnn_last_error(const tmpnn_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
-int tmpnn_load_weights(tmpnn_ctx* ctx, const float* host_blob, int64_t n_floats) {
+int tmpnn_load_weights_cfg(tmpnn_ctx* ctx, const tmpnn_model_cfg* cfg, const float* host_blob, int64_t n_floats) {
     if (!ctx) return TMPNN_E_INVALID;
+    if (!cfg || !cfg_valid(*cfg)) return fail(ctx, TMPNN_E_INVALID, "tmpnn_load_weights: invalid model configuration");
     if (!host_blob) return fail(ctx, TMPNN_E_INVALID, "tmpnn_load_weights: blob is NULL");
-    if (n_floats != tmpnn_weight_blob_floats())
+    const std::vector<RawTensor> table = build_raw_table(*cfg);
+    if (n_floats != table_floats(table))
         return fail(ctx, TMPNN_E_RANGE, "tmpnn_load_weights: blob has " + std::to_string(n_floats) + " floats, expected " +
-                                            std::to_string(tmpnn_weight_blob_floats()));
+                                            std::to_string(table_floats(table)));
     for (int64_t i = 0; i < n_floats; ++i)
         if (!std::isfinite(host_blob[i])) return fail(ctx, TMPNN_E_INVALID, "tmpnn_load_weights: non-finite weight");
-    Prep P{host_blob, ctx->raw, {}};
-    ctx->lay = prepare_weights(P);
-    CU(cudaSetDevice(ctx->device));
+    Prep P{host_blob, table, {}};
+    const DevLayout lay = prepare_weights(P, *cfg);
+    DeviceGuard guard(ctx->device);
+    if (ctx->run_pending) { CU(cudaEventSynchronize(ctx->run_ev)); ctx->run_pending = false; }
+    drop_graph(ctx);
     if (ctx->d_weights) cudaFree(ctx->d_weights);
     ctx->d_weights = nullptr;
     ctx->have_weights = false;
     CU(cudaMalloc(&ctx->d_weights, P.dev.size() * sizeof(float)));
+    ++g_realloc_count;
     CU(cudaMemcpyAsync(ctx->d_weights, P.dev.data(), P.dev.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    ctx->cfg = *cfg;
+    ctx->raw = table;
+    ctx->lay = lay;
     ctx->have_weights = true;
     return TMPNN_OK;
 }
 
-int tmpnn_run_batch(tmpnn_ctx* ctx, int32_t B, const int32_t* offsets, const float* X, const int32_t* S,
-                    const int32_t* residue_idx, const int32_t* chain_enc, const uint8_t* mask, float* out_table,
-                    uint32_t flags, void* stream_) {
+int tmpnn_load_weights(tmpnn_ctx* ctx, const float* host_blob, int64_t n_floats) {
+    const tmpnn_model_cfg c = default_model_cfg();
+    return tmpnn_load_weights_cfg(ctx, &c, host_blob, n_floats);
+}
+
+int tmpnn_run_batch_ex(tmpnn_ctx* ctx, int32_t B, const int32_t* offsets, const float* X, const int32_t* S,
+                       const int32_t* residue_idx, const int32_t* chain_enc, const uint8_t* mask, float* out_table,
+                       float* out_log_probs, uint32_t flags, void* stream_) {
     if (!ctx) return TMPNN_E_INVALID;
     if (!ctx->have_weights) return fail(ctx, TMPNN_E_NOWEIGHTS, "tmpnn_run_batch: weights not loaded");
-    if (B <= 0 || !offsets || !X || !S || !residue_idx || !chain_enc || !mask || !out_table)
+    if (B <= 0 || !offsets || !X || !S || !residue_idx || !chain_enc || !mask)
         return fail(ctx, TMPNN_E_INVALID, "tmpnn_run_batch: NULL pointer or B <= 0");
+    if (!out_table && !out_log_probs) return fail(ctx, TMPNN_E_INVALID, "tmpnn_run_batch: no output requested");
+    if (out_table && !ctx->cfg.has_head)
+        return fail(ctx, TMPNN_E_INVALID, "tmpnn_run_batch: the loaded model has no ddG head (has_head = 0); ask for log_probs only");
     if (offsets[0] != 0) return fail(ctx, TMPNN_E_INVALID, "tmpnn_run_batch: offsets[0] must be 0");
     int lmax = 0;
     for (int b = 0; b < B; ++b) {
@@ -551,10 +863,15 @@ int tmpnn_run_batch(tmpnn_ctx* ctx, int32_t B, const int32_t* offsets, const flo
         for (int i = 0; i < N; ++i)
             if (S[i] < 0 || S[i] > 20) return fail(ctx, TMPNN_E_RANGE, "tmpnn_run_batch: S[" + std::to_string(i) + "] outside 0..20");
     }
-    CU(cudaSetDevice(ctx->device));
+    DeviceGuard guard(ctx->device);
     cudaStream_t st = stream_ ? (cudaStream_t)stream_ : ctx->stream;
+    // a previous TMPNN_NO_SYNC call may have left a range error behind
+    if (ctx->run_pending && cudaEventQuery(ctx->run_ev) == cudaSuccess) {
+        ctx->run_pending = false;
+        if (int rc = take_range_error(ctx)) return rc;
+    }
 
-    // ---- inputs -------------------------------------------------------------
+    // ---- inputs: one packed staging buffer -> one H2D -------------------------------
     const size_t o_off = 0;
     const size_t o_X = align16(o_off + (size_t)(B + 1) * 4);
     const size_t o_S = align16(o_X + (size_t)N * 48);
@@ -567,6 +884,7 @@ int tmpnn_run_batch(tmpnn_ctx* ctx, int32_t B, const int32_t* offsets, const flo
         CU(cudaEventSynchronize(ctx->stage_ev));
         ctx->stage_busy = false;
     }
+    const uint64_t realloc0 = g_realloc_count;
     CU(ctx->d_in.reserve(used));
     if (ctx->h_stage_cap < used) {
         if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
@@ -574,158 +892,123 @@ int tmpnn_run_batch(tmpnn_ctx* ctx, int32_t B, const int32_t* offsets, const flo
         ctx->h_stage_cap = 0;
         CU(cudaMallocHost(&ctx->h_stage, used + used / 4));
         ctx->h_stage_cap = used + used / 4;
+        ++g_realloc_count;
     }
     std::memcpy(ctx->h_stage + o_off, offsets, (size_t)(B + 1) * 4);
-    const int* d_off = reinterpret_cast<const int*>(ctx->d_in.p + o_off);
-    const float* d_X = X;
-    const int *d_S = S, *d_r = residue_idx, *d_c = chain_enc;
-    const uint8_t* d_m = mask;
+    RunIO io{};
+    io.B = B; io.N = N; io.lmax = lmax; io.stage_bytes = used;
+    io.off = reinterpret_cast<const int*>(ctx->d_in.p + o_off);
+    io.X = X; io.S = S; io.r = residue_idx; io.c = chain_enc; io.m = mask;
     if (!in_dev) {
         std::memcpy(ctx->h_stage + o_X, X, (size_t)N * 48);
         std::memcpy(ctx->h_stage + o_S, S, (size_t)N * 4);
         std::memcpy(ctx->h_stage + o_r, residue_idx, (size_t)N * 4);
         std::memcpy(ctx->h_stage + o_c, chain_enc, (size_t)N * 4);
         std::memcpy(ctx->h_stage + o_m, mask, (size_t)N);
-        d_X = reinterpret_cast<const float*>(ctx->d_in.p + o_X);
-        d_S = reinterpret_cast<const int*>(ctx->d_in.p + o_S);
-        d_r = reinterpret_cast<const int*>(ctx->d_in.p + o_r);
-        d_c = reinterpret_cast<const int*>(ctx->d_in.p + o_c);
-        d_m = ctx->d_in.p + o_m;
+        io.X = reinterpret_cast<const float*>(ctx->d_in.p + o_X);
+        io.S = reinterpret_cast<const int*>(ctx->d_in.p + o_S);
+        io.r = reinterpret_cast<const int*>(ctx->d_in.p + o_r);
+        io.c = reinterpret_cast<const int*>(ctx->d_in.p + o_c);
+        io.m = ctx->d_in.p + o_m;
     }
-    CU(cudaMemcpyAsync(ctx->d_in.p, ctx->h_stage, used, cudaMemcpyHostToDevice, st));
-    if (!ctx->stage_ev) CU(cudaEventCreateWithFlags(&ctx->stage_ev, cudaEventDisableTiming));
-    CU(cudaEventRecord(ctx->stage_ev, st));
-    ctx->stage_busy = true;
 
     // ---- buffers --------------------------------------------------------------
     const size_t n = (size_t)N, ne = n * KNB;
-    CU(ctx->atoms.reserve(n * 16)); CU(ctx->maskf.reserve(n));
-    CU(ctx->hV.reserve(n * HID)); CU(ctx->dec_prev.reserve(n * HID)); CU(ctx->dec_last.reserve(n * HID));
-    CU(ctx->Ssum.reserve(n * HID)); CU(ctx->cnt.reserve(n)); CU(ctx->Spart.reserve(n * 3 * HID));
+    CU(ctx->atoms.reserve(n * 16)); CU(ctx->maskf.reserve(n)); CU(ctx->S_dev.reserve(n));
+    CU(ctx->hV.reserve(n * HID)); CU(ctx->dec_first.reserve(n * HID)); CU(ctx->dec_prev.reserve(n * HID));
+    CU(ctx->dec_last.reserve(n * HID)); CU(ctx->Spart.reserve(n * 3 * HID));
     CU(ctx->P.reserve(n * HID)); CU(ctx->Q.reserve(n * HID)); CU(ctx->P2.reserve(n * HID)); CU(ctx->Q2.reserve(n * HID));
     CU(ctx->E_idx.reserve(ne)); CU(ctx->D_nb.reserve(ne)); CU(ctx->hE.reserve(ne * HID));
-    float* d_table = out_table;
+#ifdef TMPNN_DEV
+    CU(ctx->Ssum.reserve(n * HID)); CU(ctx->cnt.reserve(n));
+#endif
+    io.table = out_table; io.logp = out_log_probs;
     if (!out_dev) {
-        CU(ctx->table.reserve(n * 21));
-        d_table = ctx->table.p;
+        if (out_table) { CU(ctx->table.reserve(n * 21)); io.table = ctx->table.p; io.host_table = out_table; }
+        if (out_log_probs) { CU(ctx->logp.reserve(n * 21)); io.logp = ctx->logp.p; io.host_logp = out_log_probs; }
     }
+    if (g_realloc_count != realloc0) ctx->buf_epoch = g_realloc_count;
     ctx->last_N = N;
-    ctx->last_table = d_table;
+    ctx->last_table = io.table;
+    ctx->last_logp = io.logp;
 
-    const float* W = ctx->d_weights;
-    const DevLayout& L = ctx->lay;
-    const int npt = choose_npt(N, ctx->sm_count);
-    const int stop = ctx->debug_stop;
-    bool done = false;
-    auto stage_done = [&](int s) { if (stop == s) done = true; return done; };
+    // runs on one context are ordered even across streams (they share the buffers above)
+    if (ctx->run_pending) CU(cudaStreamWaitEvent(st, ctx->run_ev, 0));
+    if (ctx->clear_err) { CU(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), st)); ctx->clear_err = false; }
+    CU(cudaMemcpyAsync(ctx->d_in.p, ctx->h_stage, io.stage_bytes, cudaMemcpyHostToDevice, st));   // ONE copy for all inputs
+    CU(cudaEventRecord(ctx->stage_ev, st));
+    ctx->stage_busy = true;
 
-    // ---- pipeline ---------------------------------------------------------------
-    // (h_V starts at zero, protein_mpnn_utils.py:1225; cleared up front so that no memset sits between two kernels
-    // of the programmatic-dependent-launch chain)
-    CU(cudaMemsetAsync(ctx->hV.p, 0, n * HID * sizeof(float), st));
-    { LaunchScope ls(ctx, st, "knn");
-      launch_knn(d_off, B, d_X, d_m, N, lmax, ctx->atoms.p, ctx->maskf.p, ctx->E_idx.p, ctx->D_nb.p, st); }
-    if (!stage_done(1)) {
-        if (ctx->tc_mask & 1) {
-            LaunchScope ls(ctx, st, "tc_edge_feat");
-            launch_tc_edge_feat(ctx->atoms.p, ctx->E_idx.p, ctx->D_nb.p, d_r, d_c, W + L.pos_table, W + L.rbf_mu, W + L.tc_feat,
-                                W + L.ne.g, W + L.ne.b, W + L.be, ctx->hE.p, N, ctx->sm_count, st);
-        } else {
-            LaunchScope ls(ctx, st, "edge_feat");
-            launch_edge_feat(npt, ctx->atoms.p, ctx->E_idx.p, ctx->D_nb.p, d_r, d_c, W + L.pos_table, W + L.rbf_mu,
-                             W + L.feat, W + L.ne.g, W + L.ne.b, W + L.be, ctx->hE.p, N, st);
-        }
-    }
-    if (!done && !stage_done(2)) {
-        for (int l = 0; l < 3 && !done; ++l) {
-            const EncW& e = L.enc[l];
-            {   // first layer: h_V = 0, so P_i = b1 and Q_j = 0 (one shared row each, stride 0)
-                const float* Pp = l == 0 ? W + e.b1 : ctx->P.p;
-                const float* Qp = l == 0 ? W + L.zeros : ctx->Q.p;
-                const int stride = l == 0 ? 0 : HID;
-                if (ctx->tc_mask & 2) {
-                    LaunchScope ls(ctx, st, "tc_enc_msg");
-                    launch_tc_msg(false, ctx->hE.p, ctx->E_idx.p, Pp, stride, Qp, stride, ctx->maskf.p, W + e.tc_msg, W + e.b2,
-                                  ctx->Spart.p, N, ctx->sm_count, st, l == 1 ? ctx->d_trace : nullptr);
-                } else {
-                    LaunchScope ls(ctx, st, "enc_msg");
-                    launch_msg(npt, false, ctx->hE.p, ctx->E_idx.p, Pp, stride, Qp, stride, ctx->maskf.p, W + e.msg, W + e.b2,
-                               ctx->Ssum.p, ctx->cnt.p, N, st);
+    // ---- the kernel chain: launched directly, or replayed from the graph captured for this call shape ----
+    GraphKey key;
+    key.B = B; key.N = N; key.lmax = lmax; key.stop = ctx->debug_stop; key.flags = flags; key.epoch = ctx->buf_epoch;
+    key.ptr[0] = in_dev ? X : nullptr; key.ptr[1] = in_dev ? S : nullptr; key.ptr[2] = in_dev ? residue_idx : nullptr;
+    key.ptr[3] = in_dev ? chain_enc : nullptr; key.ptr[4] = in_dev ? mask : nullptr;
+    key.ptr[5] = out_table; key.ptr[6] = out_log_probs;
+    const bool graph_ok = ctx->graphs && !ctx->profiling && !ctx->d_trace;
+    bool launched = false;
+    if (graph_ok && ctx->graph_exec && ctx->graph_key == key) {
+        CU(cudaGraphLaunch(ctx->graph_exec, st));
+        ctx->launches += ctx->graph_kernels;
+        ctx->graph_launches++;
+        launched = true;
+    } else if (graph_ok && ctx->last_key == key) {
+        // the same call shape twice in a row: capture the chain (kernels launched under capture do not run)
+        drop_graph(ctx);
+        const int64_t l0 = ctx->launches;
+        cudaGraph_t g = nullptr;
+        cudaError_t ce = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+        if (ce == cudaSuccess) {
+            const int rc = enqueue_pipeline(ctx, io, st);
+            ce = cudaStreamEndCapture(st, &g);
+            if (rc == TMPNN_OK && ce == cudaSuccess && g) {
+                ce = cudaGraphInstantiate(&ctx->graph_exec, g, 0);
+                if (ce == cudaSuccess) {
+                    ctx->graph_key = key;
+                    ctx->graph_kernels = ctx->launches - l0;
+                    ctx->launches = l0;
                 }
             }
-            NodeUpdArgs a{};
-            a.weights = W; a.w = e.nu; a.Ssum = ctx->Ssum.p; a.cnt = ctx->cnt.p; a.hV = ctx->hV.p; a.hV_copy = nullptr;
-            a.Spart = (ctx->tc_mask & 2) ? ctx->Spart.p : nullptr; a.E_idx = ctx->E_idx.p; a.enc = 1;
-            a.maskf = ctx->maskf.p; a.S = d_S; a.N = N;
-            a.trace = (l == 1 && ctx->d_trace) ? ctx->d_trace + 1024 : nullptr;
-            a.proj[0] = {e.b11, -1, ctx->P2.p};     // edge update of this layer
-            a.proj[1] = {-1, -1, ctx->Q2.p};
-            if (l < 2) {
-                const EncW& nx = L.enc[l + 1];
-                a.proj[2] = {nx.b1, -1, ctx->P.p};
-                a.proj[3] = {-1, -1, ctx->Q.p};
-            } else {
-                const DecW& nx = L.dec[0];
-                a.proj[2] = {nx.b1, -1, ctx->P.p};
-                a.proj[3] = {-1, nx.Tseq, ctx->Q.p};
-            }
-            a.nproj = 4;
-            { LaunchScope ls(ctx, st, "node_update"); launch_node_update(a, ctx->sm_count, st); }
-            if (ctx->tc_mask & 4) {
-                LaunchScope ls(ctx, st, "tc_edge_upd");
-                launch_tc_edge_upd(ctx->hE.p, ctx->E_idx.p, ctx->P2.p, ctx->Q2.p, ctx->maskf.p, W + e.tc_edge, W + e.b12, W + e.b13,
-                                   W + e.n3.g, W + e.n3.b, N, ctx->sm_count, st, (l == 1 && ctx->d_trace) ? ctx->d_trace + 512 : nullptr);
-            } else {
-                LaunchScope ls(ctx, st, "edge_upd");
-                launch_edge_upd(npt, ctx->hE.p, ctx->E_idx.p, ctx->P2.p, ctx->Q2.p, W + e.edge, W + e.b12, W + e.b13,
-                                W + e.n3.g, W + e.n3.b, N, st);
-            }
-            stage_done(3 + l);
+            if (g) cudaGraphDestroy(g);
+        }
+        if (ctx->graph_exec) {
+            CU(cudaGraphLaunch(ctx->graph_exec, st));
+            ctx->launches += ctx->graph_kernels;
+            ctx->graph_launches++;
+            launched = true;
+        } else {
+            (void)cudaGetLastError();       // capture is an optimisation: fall back to direct launches
+            ctx->launches = l0;
+            ctx->graphs = false;
         }
     }
-    if (!done) {
-        for (int l = 0; l < 3 && !done; ++l) {
-            const DecW& d = L.dec[l];
-            if (ctx->tc_mask & 2) {
-                LaunchScope ls(ctx, st, "tc_dec_msg");
-                launch_tc_msg(true, ctx->hE.p, ctx->E_idx.p, ctx->P.p, HID, ctx->Q.p, HID, ctx->maskf.p, W + d.tc_msg, W + d.b2,
-                              ctx->Spart.p, N, ctx->sm_count, st);
-            } else {
-                LaunchScope ls(ctx, st, "dec_msg");
-                launch_msg(npt, true, ctx->hE.p, ctx->E_idx.p, ctx->P.p, HID, ctx->Q.p, HID, ctx->maskf.p, W + d.msg,
-                           W + d.b2, ctx->Ssum.p, ctx->cnt.p, N, st);
-            }
-            NodeUpdArgs a{};
-            a.weights = W; a.w = d.nu; a.Ssum = ctx->Ssum.p; a.cnt = ctx->cnt.p; a.hV = ctx->hV.p;
-            a.Spart = (ctx->tc_mask & 2) ? ctx->Spart.p : nullptr; a.E_idx = ctx->E_idx.p; a.enc = 0;
-            a.hV_copy = (l == 1) ? ctx->dec_prev.p : (l == 2 ? ctx->dec_last.p : nullptr);
-            a.maskf = ctx->maskf.p; a.S = d_S; a.N = N;
-            a.nproj = 0;
-            if (l < 2) {
-                const DecW& nx = L.dec[l + 1];
-                a.proj[0] = {nx.b1, -1, ctx->P.p};
-                a.proj[1] = {-1, nx.Tseq, ctx->Q.p};
-                a.nproj = 2;
-            }
-            { LaunchScope ls(ctx, st, "node_update"); launch_node_update(a, ctx->sm_count, st); }
-            stage_done(6 + l);
-        }
+    ctx->last_key = key;
+    if (!launched) {
+        if (int rc = enqueue_pipeline(ctx, io, st)) return rc;
     }
-    if (!done) {
-        HeadArgs h{};
-        h.weights = W; h.stream = L.head; h.Ws = L.Ws; h.la_b = L.la_b; h.m1_b = L.m1_b; h.m2_b = L.m2_b;
-        h.m3_b = L.m3_b; h.ddg = L.ddg;
-        h.dec_last = ctx->dec_last.p; h.dec_prev = ctx->dec_prev.p; h.S = d_S; h.table = d_table; h.N = N;
-        { LaunchScope ls(ctx, st, "head"); launch_head(h, ctx->sm_count, st); }
-        if (!out_dev) CU(cudaMemcpyAsync(out_table, d_table, n * 21 * sizeof(float), cudaMemcpyDeviceToHost, st));
-    }
-    CU(cudaGetLastError());
-    CU(tc_take_error());
+    CU(cudaEventRecord(ctx->run_ev, st));
+    ctx->run_pending = true;
     if (!(flags & TMPNN_NO_SYNC) || !out_dev) {
         CU(cudaStreamSynchronize(st));
         ctx->stage_busy = false;
+        ctx->run_pending = false;
         if (ctx->profiling) drain_profile(ctx);
+        if (int rc = take_range_error(ctx)) return rc;
     }
+    return TMPNN_OK;
+}
+
+int tmpnn_run_batch(tmpnn_ctx* ctx, int32_t B, const int32_t* offsets, const float* X, const int32_t* S,
+                    const int32_t* residue_idx, const int32_t* chain_enc, const uint8_t* mask, float* out_table,
+                    uint32_t flags, void* stream_) {
+    if (ctx && !out_table) return fail(ctx, TMPNN_E_INVALID, "tmpnn_run_batch: NULL pointer or B <= 0");
+    return tmpnn_run_batch_ex(ctx, B, offsets, X, S, residue_idx, chain_enc, mask, out_table, nullptr, flags, stream_);
+}
+
+int tmpnn_set_graphs(tmpnn_ctx* ctx, int enabled) {
+    if (!ctx) return TMPNN_E_INVALID;
+    ctx->graphs = enabled != 0;
+    if (!ctx->graphs) { DeviceGuard guard(ctx->device); drop_graph(ctx); }
     return TMPNN_OK;
 }
 
@@ -740,16 +1023,18 @@ int tmpnn_fetch(tmpnn_ctx* ctx, const char* name, void* host_dst, int64_t bytes)
     else if (s == "D_nb") { src = ctx->D_nb.p; sz = n * KNB * 4; }
     else if (s == "h_E") { src = ctx->hE.p; sz = n * KNB * HID * 4; }
     else if (s == "h_V") { src = ctx->hV.p; sz = n * HID * 4; }
+    else if (s == "dec0") { src = ctx->dec_first.p; sz = n * HID * 4; }
     else if (s == "dec1") { src = ctx->dec_prev.p; sz = n * HID * 4; }
     else if (s == "dec2") { src = ctx->dec_last.p; sz = n * HID * 4; }
-    else if (s == "table") { src = ctx->last_table; sz = n * 21 * 4; }
+    else if (s == "table" && ctx->last_table) { src = ctx->last_table; sz = n * 21 * 4; }
+    else if (s == "log_probs" && ctx->last_logp) { src = ctx->last_logp; sz = n * 21 * 4; }
     else if (s == "tc_trace" && ctx->d_trace) { src = ctx->d_trace; sz = 2 * 512 * sizeof(long long); }
     else if (s == "node_trace" && ctx->d_trace) { src = ctx->d_trace + 1024; sz = 64 * sizeof(long long); }
     else return fail(ctx, TMPNN_E_NOTFOUND, "tmpnn_fetch: unknown tensor '" + s + "'");
     if ((size_t)bytes != sz)
         return fail(ctx, TMPNN_E_RANGE, "tmpnn_fetch: '" + s + "' is " + std::to_string(sz) + " bytes, caller gave " + std::to_string(bytes));
-    CU(cudaSetDevice(ctx->device));
-    CU(cudaStreamSynchronize(ctx->stream));
+    DeviceGuard guard(ctx->device);
+    if (ctx->run_pending) { CU(cudaEventSynchronize(ctx->run_ev)); ctx->run_pending = false; }   // whichever stream the last run used
     CU(cudaMemcpy(host_dst, src, sz, cudaMemcpyDeviceToHost));
     return TMPNN_OK;
 }
@@ -768,6 +1053,7 @@ int tmpnn_set_profiling(tmpnn_ctx* ctx, int enabled) {
 
 int tmpnn_profile_count(tmpnn_ctx* ctx) {
     if (!ctx) return TMPNN_E_INVALID;
+    DeviceGuard guard(ctx->device);
     drain_profile(ctx);   // blocks until the recorded events have completed
     return (int)ctx->prof.size();
 }
@@ -782,12 +1068,16 @@ int tmpnn_profile_get(tmpnn_ctx* ctx, int index, const char** kernel_name, doubl
 
 int tmpnn_profile_reset(tmpnn_ctx* ctx) {
     if (!ctx) return TMPNN_E_INVALID;
+    DeviceGuard guard(ctx->device);
     drain_profile(ctx);
     ctx->prof.clear();
     ctx->launches = 0;
+    ctx->graph_launches = 0;
     return TMPNN_OK;
 }
 
 int64_t tmpnn_launch_count(const tmpnn_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int64_t tmpnn_graph_launch_count(const tmpnn_ctx* ctx) { return ctx ? ctx->graph_launches : 0; }
 
 }  // extern "C"

@@ -1,4 +1,4 @@
-// Host-visible launch interface of kernels.cu.
+// Host-visible launch interface of the kernel files (knn_kernel.cu, tc_edge_kernels.cu, node_kernels.cu, head_kernels.cu).
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -41,15 +41,45 @@ struct HeadArgs {
     int N;
 };
 
+// Generic head (any cfg.model.{num_final_layers, lightattn, hidden_dims}, transfer_model.py:45-73,96-116)
+struct HeadGenArgs {
+    const float* weights;
+    int nlayers;                    // LightAttention centre tap (no ReLU in front) + the both_out Linears (ReLU in front)
+    int in_dim[TMPNN_MAX_HIDDEN + 2], out_dim[TMPNN_MAX_HIDDEN + 2];
+    int64_t w[TMPNN_MAX_HIDDEN + 2], b[TMPNN_MAX_HIDDEN + 2];
+    int relu_first;                 // 0: layer 0 is LightAttention (applied to the raw input)
+    int64_t Ws, ddg;
+    const float* dec[3];            // decoder states, last layer first; only the first num_final are read
+    int num_final;
+    const int* S;
+    float* table;                   // [N][21]
+    int N;
+};
+
+// ProteinMPNN's own output layer: log_softmax(W_out . h_V + b)   (protein_mpnn_utils.py:1275-1276)
+struct LogProbArgs {
+    const float* weights;
+    int64_t Wout, bout;
+    const float* hV;                // [N][128] last decoder state
+    float* out;                     // [N][21]
+    int N;
+};
+
 cudaError_t kernels_init();
+cudaError_t head_kernels_init();
 cudaError_t node_kernels_init();
 cudaError_t tc_kernels_init();
 cudaError_t tc_take_error();   // sticky host-side error of the tensor-core launchers (tensor-map encoding), cleared on read
 int knn_max_len();
 
 // first kernel of a call: per-residue atoms (N, CA, C, O, virtual C-beta) and float mask, then the k-NN graph
-void launch_knn(const int* offsets, int B, const float* X, const uint8_t* mask, int N, int lmax, float* atoms, float* maskf,
-                int* E_idx, float* D_nb, cudaStream_t st);
+// (also writes S_out = S clamped to 0..20 and raises *err_flag when it had to clamp)
+void launch_knn(const int* offsets, int B, const float* X, const uint8_t* mask, const int* S_in, int N, int lmax, float* atoms,
+                float* maskf, int* S_out, int* err_flag, int* E_idx, float* D_nb, cudaStream_t st);
+void launch_head_generic(const HeadGenArgs& a, cudaStream_t st);
+void launch_log_probs(const LogProbArgs& a, cudaStream_t st);
+#ifdef TMPNN_DEV   // FP32 SIMT generation of the edge kernels (simt_edge_kernels.cu), bring-up only
+cudaError_t simt_kernels_init();
 void launch_edge_feat(int npt, const float* atoms, const int* E_idx, const float* D_nb, const int* ridx,
                       const int* cenc, const float* pos_table, const float* rbf_mu, const float* wstream,
                       const float* ln_g, const float* ln_b, const float* b_e, float* hE, int N, cudaStream_t st);
@@ -59,6 +89,7 @@ void launch_msg(int npt, bool dec, const float* hE, const int* E_idx, const floa
 void launch_edge_upd(int npt, float* hE, const int* E_idx, const float* P, const float* Q, const float* wstream,
                      const float* b12, const float* b13, const float* ln_g, const float* ln_b, int N,
                      cudaStream_t st);
+#endif
 void launch_tc_edge_upd(float* hE, const int* E_idx, const float* P, const float* Q, const float* maskf, const float* wimg,
                         const float* b12, const float* b13, const float* ln_g, const float* ln_b, int N, int sms, cudaStream_t st,
                         long long* trace = nullptr);

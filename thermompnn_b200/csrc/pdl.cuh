@@ -3,7 +3,7 @@
 // launching once all our CTAs have started) and pdl_wait() before it first touches data written by earlier kernels
 // (returns when the predecessor grid has completed and its writes are visible).  What runs before pdl_wait() may
 // only read constants (weights) and set up shared memory / TMEM.  Ordering is transitive: a grid cannot complete
-// before its own pdl_wait() has returned.  TMPNN_PDL=0 turns the launch attribute off (plain stream order).
+// before its own pdl_wait() has returned.  (-DTMPNN_DEV builds: TMPNN_PDL=0 turns the launch attribute off, for A/B timing.)
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdlib>
@@ -15,8 +15,12 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 inline bool pdl_enabled() {
+#ifdef TMPNN_DEV
     static const bool on = [] { const char* e = std::getenv("TMPNN_PDL"); return !(e && std::atoi(e) == 0); }();
     return on;
+#else
+    return true;
+#endif
 }
 
 template <typename... KArgs, typename... Args>

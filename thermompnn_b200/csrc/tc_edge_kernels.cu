@@ -26,33 +26,13 @@ using namespace tc;
 namespace {
 
 constexpr int TC_ROWS = 128;
-constexpr int TC_THREADS = 224;
 constexpr int TC_WSLOTS = 3;
 constexpr uint32_t TC_WCHUNK_BYTES = 32768;   // [128 n][32 k] hi (16 KB) | lo (16 KB)
 constexpr uint32_t COL_D0 = 0, COL_D1 = 128, COL_AHI = 256, COL_ALO = 384;
 
-struct __align__(1024) TcSmem {
-    uint8_t wring[TC_WSLOTS][TC_WCHUNK_BYTES];   // 96 KB
-    float hE[4][TC_ROWS * 32];                   // 64 KB: four [128 rows][32 floats] slabs, 16-byte chunks XOR (row & 7)
-    float q[2][TC_ROWS * 32];                    // 32 KB: gathered Q rows, one 32-column chunk per buffer
-    float p[4][HID];                             // P rows of the (up to 4) residues the tile touches
-    float vec[4][HID];                           // per-kernel vectors (biases, LayerNorm gain/shift)
-    int jidx[TC_ROWS];
-    float wrow[TC_ROWS];                          // message weight of the row (0 for unused slots / rows past the end)
-    float mrow[TC_ROWS];                          // mask of the row's own residue
-    uint64_t w_full[TC_WSLOTS], w_empty[TC_WSLOTS];
-    uint64_t a_ready[4];                          // A chunk c written by all 128 epilogue threads
-    uint64_t d_ready[2];                          // accumulator buffer complete
-    uint64_t he_full, he_empty;
-    uint64_t q_full[2], q_empty[2];
-    uint32_t tmem_base;
-};
-
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-
 __device__ __forceinline__ uint32_t rna_tf32(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -62,30 +42,6 @@ __device__ __forceinline__ uint32_t rna_tf32(float x) {
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
     hi = rna_tf32(x);
     lo = rna_tf32(x - __uint_as_float(hi));
-}
-
-// float offset of 16-byte chunk j (0..7) of row r inside a [128][32] swizzled slab
-__device__ __forceinline__ int slab_off(int r, int j) { return r * 32 + ((j ^ (r & 7)) << 2); }
-
-__device__ __forceinline__ void load_row_chunk(float (&v)[32], const float* slab, int r) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        float4 t = *reinterpret_cast<const float4*>(slab + slab_off(r, j));
-        v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
-    }
-}
-// the same for an activation chunk filled by per-row bulk copies (row pitch ACT_PITCH floats, no swizzle)
-__device__ __forceinline__ void load_act_row(float (&v)[32], const float* chunk, int r) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        float4 t = *reinterpret_cast<const float4*>(chunk + r * 36 + j * 4);
-        v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
-    }
-}
-__device__ __forceinline__ void store_row_chunk(float* slab, int r, const float (&v)[32]) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-        *reinterpret_cast<float4*>(slab + slab_off(r, j)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
 }
 
 // Write 32 values as columns [32c, 32c+32) of the next A operand (hi and lo planes) and publish the chunk.

@@ -13,6 +13,8 @@
 #include <string>
 #include <vector>
 
+#include "../../include/thermompnn_b200.h"
+
 namespace tmpnn {
 
 constexpr int KNB = 48;     // neighbour slots per residue (checkpoint num_edges, transfer_model.py:26)
@@ -29,7 +31,27 @@ struct RawTensor {
     int64_t offset;
 };
 
-inline std::vector<RawTensor> build_raw_table() {
+inline tmpnn_model_cfg default_model_cfg() {
+    tmpnn_model_cfg c{};
+    c.num_final_layers = 2; c.lightattn = 1; c.n_hidden = 2; c.hidden_dims[0] = 64; c.hidden_dims[1] = 32; c.has_head = 1;
+    return c;
+}
+inline bool cfg_valid(const tmpnn_model_cfg& c) {
+    if (c.has_head != 0 && c.has_head != 1) return false;
+    if (!c.has_head) return true;
+    if (c.num_final_layers < 0 || c.num_final_layers > 3 || c.n_hidden < 0 || c.n_hidden > TMPNN_MAX_HIDDEN) return false;
+    if (c.lightattn != 0 && c.lightattn != 1) return false;
+    for (int i = 0; i < c.n_hidden; ++i)
+        if (c.hidden_dims[i] < 1 || c.hidden_dims[i] > 512) return false;
+    return true;
+}
+inline bool cfg_is_default(const tmpnn_model_cfg& c) {
+    return c.has_head == 1 && c.num_final_layers == 2 && c.lightattn == 1 && c.n_hidden == 2 && c.hidden_dims[0] == 64 &&
+           c.hidden_dims[1] == 32;
+}
+inline int head_in_dim(const tmpnn_model_cfg& c) { return HID * c.num_final_layers + HID; }   // transfer_model.py:58
+
+inline std::vector<RawTensor> build_raw_table(const tmpnn_model_cfg& cfg) {
     std::vector<RawTensor> t;
     int64_t off = 0;
     auto add = [&](const std::string& n, int r, int c) {
@@ -74,11 +96,21 @@ inline std::vector<RawTensor> build_raw_table() {
     }
     add(pm + "W_out.weight", 21, 128);
     add(pm + "W_out.bias", 1, 21);
-    add("light_attention.feature_convolution.weight_center", 384, 384);
-    add("light_attention.feature_convolution.bias", 1, 384);
-    add("both_out.1.weight", 64, 384); add("both_out.1.bias", 1, 64);
-    add("both_out.3.weight", 32, 64);  add("both_out.3.bias", 1, 32);
-    add("both_out.5.weight", 21, 32);  add("both_out.5.bias", 1, 21);
+    if (!cfg.has_head) return t;
+    // head (transfer_model.py:58-73): hid_sizes = [128 F + 128] + hidden_dims + [21]; both_out = (ReLU, Linear) per pair
+    const int din = head_in_dim(cfg);
+    if (cfg.lightattn) {
+        add("light_attention.feature_convolution.weight_center", din, din);
+        add("light_attention.feature_convolution.bias", 1, din);
+    }
+    int prev = din;
+    for (int i = 0; i <= cfg.n_hidden; ++i) {
+        const int out = i < cfg.n_hidden ? cfg.hidden_dims[i] : 21;
+        const std::string p = "both_out." + std::to_string(2 * i + 1);
+        add(p + ".weight", out, prev);
+        add(p + ".bias", 1, out);
+        prev = out;
+    }
     add("ddg_out.weight", 1, 1);
     add("ddg_out.bias", 1, 1);
     return t;
@@ -123,9 +155,15 @@ struct DevLayout {
     EncW enc[3];
     DecW dec[3];
     int64_t Ws;             // [21][128] embedding rows
+    int64_t Wout, bout;     // ProteinMPNN W_out [21][128] row-major and its bias (log_probs)
+    // default-cfg head (specialised kernels):
     int64_t head;           // KN chunks: LA column blocks 0..2 (12 each) | both_out.1 (12) | .3 (2) | .5 (1), padded to 128 cols
     int64_t la_b, m1_b, m2_b, m3_b;
     int64_t ddg;            // [2] = scale, shift
+    // any other cfg (generic head kernel): nn.Linear weights as stored, [out][in] row-major
+    int32_t gen_layers;     // LightAttention (if any) + the both_out Linears
+    int32_t gen_in[TMPNN_MAX_HIDDEN + 2], gen_out[TMPNN_MAX_HIDDEN + 2];
+    int64_t gen_w[TMPNN_MAX_HIDDEN + 2], gen_b[TMPNN_MAX_HIDDEN + 2];
     int64_t zeros;          // [128] zeros (Q for the first encoder layer)
     int64_t total;
 };

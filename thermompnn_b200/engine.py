@@ -12,7 +12,9 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libthermompnn_b200.so")
+# TMPNN_LIB=dev selects the development build (-DTMPNN_DEV: SIMT edge kernels, TMPNN_TC / TMPNN_PDL / TMPNN_TC_TRACE switches)
+LIB_PATH = os.path.join(_HERE, "libthermompnn_b200_dev.so" if os.environ.get("TMPNN_LIB") == "dev" else "libthermompnn_b200.so")
+MAX_HIDDEN = 8
 
 IN_DEVICE, OUT_DEVICE, NO_SYNC = 1, 2, 4
 
@@ -21,8 +23,29 @@ SYMBOLS = [
     "tmpnn_abi_version", "tmpnn_create", "tmpnn_destroy", "tmpnn_last_error", "tmpnn_weight_count",
     "tmpnn_weight_info", "tmpnn_weight_blob_floats", "tmpnn_load_weights", "tmpnn_run_batch", "tmpnn_fetch",
     "tmpnn_set_debug_stop", "tmpnn_set_profiling", "tmpnn_profile_count", "tmpnn_profile_get",
-    "tmpnn_profile_reset", "tmpnn_launch_count",
+    "tmpnn_profile_reset", "tmpnn_launch_count", "tmpnn_graph_launch_count", "tmpnn_default_cfg", "tmpnn_cfg_weight_count",
+    "tmpnn_cfg_weight_info", "tmpnn_cfg_weight_blob_floats", "tmpnn_load_weights_cfg", "tmpnn_run_batch_ex", "tmpnn_set_graphs",
 ]
+
+
+class ModelCfg(C.Structure):
+    """``tmpnn_model_cfg``: which head a checkpoint carries (cfg.model.* of transfer_model.py:45-73)."""
+    _fields_ = [("num_final_layers", C.c_int32), ("lightattn", C.c_int32), ("n_hidden", C.c_int32),
+                ("hidden_dims", C.c_int32 * MAX_HIDDEN), ("has_head", C.c_int32)]
+
+    @classmethod
+    def make(cls, num_final_layers=2, lightattn=True, hidden_dims=(64, 32), has_head=True) -> "ModelCfg":
+        hidden_dims = list(hidden_dims)
+        if len(hidden_dims) > MAX_HIDDEN:
+            raise ValueError(f"at most {MAX_HIDDEN} hidden layers")
+        c = cls()
+        c.num_final_layers, c.lightattn, c.n_hidden, c.has_head = int(num_final_layers), int(bool(lightattn)), len(hidden_dims), int(bool(has_head))
+        for i, d in enumerate(hidden_dims):
+            c.hidden_dims[i] = int(d)
+        return c
+
+    def key(self):
+        return (self.num_final_layers, self.lightattn, tuple(self.hidden_dims[:self.n_hidden]), self.has_head)
 
 _lib = None
 
@@ -61,26 +84,43 @@ def load_library() -> C.CDLL:
     lib.tmpnn_profile_reset.argtypes = [vp]
     lib.tmpnn_launch_count.argtypes = [vp]
     lib.tmpnn_launch_count.restype = i64
+    lib.tmpnn_graph_launch_count.argtypes = [vp]
+    lib.tmpnn_graph_launch_count.restype = i64
+    cfgp = C.POINTER(ModelCfg)
+    lib.tmpnn_default_cfg.argtypes = [cfgp]
+    lib.tmpnn_default_cfg.restype = None
+    lib.tmpnn_cfg_weight_count.argtypes = [cfgp]
+    lib.tmpnn_cfg_weight_info.argtypes = [cfgp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(i64), C.POINTER(i32), C.POINTER(i32)]
+    lib.tmpnn_cfg_weight_blob_floats.argtypes = [cfgp]
+    lib.tmpnn_cfg_weight_blob_floats.restype = i64
+    lib.tmpnn_load_weights_cfg.argtypes = [vp, cfgp, vp, i64]
+    lib.tmpnn_run_batch_ex.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, u32, vp]
+    lib.tmpnn_set_graphs.argtypes = [vp, C.c_int]
     _lib = lib
     return lib
 
 
-def weight_table() -> List[Tuple[str, int, int, int]]:
-    """[(name, offset, rows, cols)] of the raw checkpoint contract (no GPU needed)."""
+def weight_table(cfg: Optional[ModelCfg] = None) -> List[Tuple[str, int, int, int]]:
+    """[(name, offset, rows, cols)] of the raw checkpoint contract for a model configuration (no GPU needed)."""
     lib = load_library()
+    cfg = cfg if cfg is not None else ModelCfg.make()
+    n = lib.tmpnn_cfg_weight_count(C.byref(cfg))
+    if n < 0:
+        raise ValueError("invalid model configuration")
     out = []
-    for i in range(lib.tmpnn_weight_count()):
+    for i in range(n):
         name, off, r, c = C.c_char_p(), C.c_int64(), C.c_int32(), C.c_int32()
-        lib.tmpnn_weight_info(i, C.byref(name), C.byref(off), C.byref(r), C.byref(c))
+        lib.tmpnn_cfg_weight_info(C.byref(cfg), i, C.byref(name), C.byref(off), C.byref(r), C.byref(c))
         out.append((name.value.decode(), off.value, r.value, c.value))
     return out
 
 
-def pack_weight_blob(state: Dict[str, np.ndarray]) -> np.ndarray:
-    """Pack a reference state_dict (``model.`` prefix stripped) into the blob ``tmpnn_load_weights`` takes."""
+def pack_weight_blob(state: Dict[str, np.ndarray], cfg: Optional[ModelCfg] = None) -> np.ndarray:
+    """Pack a reference state_dict (``model.`` prefix stripped) into the blob ``tmpnn_load_weights[_cfg]`` takes."""
     lib = load_library()
-    blob = np.zeros(lib.tmpnn_weight_blob_floats(), dtype=np.float32)
-    for name, off, r, c in weight_table():
+    cfg = cfg if cfg is not None else ModelCfg.make()
+    blob = np.zeros(lib.tmpnn_cfg_weight_blob_floats(C.byref(cfg)), dtype=np.float32)
+    for name, off, r, c in weight_table(cfg):
         if name not in state:
             raise KeyError(f"checkpoint is missing tensor '{name}'")
         v = np.asarray(state[name], dtype=np.float32)
@@ -122,15 +162,30 @@ class Engine:
         if rc != 0:
             raise EngineError(f"[{rc}] " + self._lib.tmpnn_last_error(self._ctx).decode())
 
-    def load_weights(self, blob: np.ndarray):
+    def load_weights(self, blob: np.ndarray, cfg: Optional[ModelCfg] = None):
         blob = np.ascontiguousarray(blob, dtype=np.float32)
-        self._check(self._lib.tmpnn_load_weights(self._ctx, blob.ctypes.data, blob.size))
+        cfg = cfg if cfg is not None else ModelCfg.make()
+        self._check(self._lib.tmpnn_load_weights_cfg(self._ctx, C.byref(cfg), blob.ctypes.data, blob.size))
+        self.cfg = cfg
+
+    @staticmethod
+    def _host_out(out, N, what):
+        """A caller-supplied host result array goes to C as a raw pointer: check it before that."""
+        if not (isinstance(out, np.ndarray) and out.dtype == np.float32 and out.flags.c_contiguous and out.size == N * 21):
+            raise ValueError(f"{what} must be a C-contiguous float32 array of {N} x 21 elements")
+        return out
 
     def run(self, offsets: np.ndarray, X, S, residue_idx, chain_enc, mask, out=None, *, flags: int = 0,
-            stream: int = 0):
+            stream: int = 0, log_probs=None, want_table: bool = True):
         """Run one ragged batch.  With flags == 0 every array is a host numpy array (``offsets`` always is);
-        with IN_DEVICE / OUT_DEVICE pass raw device pointers (ints) for the inputs / ``out``."""
+        with IN_DEVICE / OUT_DEVICE pass raw device pointers (ints) for the inputs / outputs.
+
+        ``out``: the [N,21] head table (allocated when None, skipped with ``want_table=False``).
+        ``log_probs``: True (allocate) / array / device pointer to also get ProteinMPNN's log-probabilities [N,21].
+        Returns the table, or (table, log_probs) when log_probs were asked for."""
         offsets = np.ascontiguousarray(offsets, dtype=np.int32)
+        if offsets.ndim != 1 or offsets.size < 2:
+            raise ValueError("offsets must be a 1-D array of B+1 entries")
         B, N = offsets.size - 1, int(offsets[-1])
         if not (flags & IN_DEVICE):
             X = np.ascontiguousarray(X, dtype=np.float32)
@@ -140,19 +195,61 @@ class Engine:
             mask = np.ascontiguousarray(mask, dtype=np.uint8)
             if not (X.size == N * 12 and S.size == N and residue_idx.size == N and chain_enc.size == N and mask.size == N):
                 raise ValueError("input array sizes do not match offsets[-1]")
-        if out is None:
-            if flags & OUT_DEVICE:
+        elif any(isinstance(a, np.ndarray) for a in (X, S, residue_idx, chain_enc, mask)):
+            raise ValueError("IN_DEVICE takes raw device pointers (ints), not host arrays")
+        dev_out = bool(flags & OUT_DEVICE)
+        copy_out = copy_lp = False
+        if not want_table:
+            out = None
+        elif out is None:
+            if dev_out:
                 raise ValueError("OUT_DEVICE needs an explicit device pointer")
-            out = np.empty((N, 21), dtype=np.float32)
-        self._check(self._lib.tmpnn_run_batch(self._ctx, B, offsets.ctypes.data, _ptr(X), _ptr(S), _ptr(residue_idx),
-                                              _ptr(chain_enc), _ptr(mask), _ptr(out), flags, stream or None))
+            # results land in a per-engine buffer with a stable address (so that repeated call shapes can replay the
+            # captured graph, whose D2H copy targets it) and are handed out as a fresh array
+            out, copy_out = self._result_buffer("table", N), True
+        elif not dev_out:
+            self._host_out(out, N, "out")
+        elif isinstance(out, np.ndarray):
+            raise ValueError("OUT_DEVICE takes a raw device pointer for `out`")
+        lp = None
+        if log_probs is not None and log_probs is not False:
+            if log_probs is True:
+                if dev_out:
+                    raise ValueError("OUT_DEVICE needs an explicit device pointer for log_probs")
+                lp, copy_lp = self._result_buffer("log_probs", N), True
+            elif not dev_out:
+                lp = self._host_out(log_probs, N, "log_probs")
+            else:
+                lp = log_probs
+        if out is None and lp is None:
+            raise ValueError("nothing to compute: want_table=False and no log_probs")
+        self._check(self._lib.tmpnn_run_batch_ex(self._ctx, B, offsets.ctypes.data, _ptr(X), _ptr(S), _ptr(residue_idx),
+                                                 _ptr(chain_enc), _ptr(mask), None if out is None else _ptr(out),
+                                                 None if lp is None else _ptr(lp), flags, stream or None))
         self._n_last = N
-        return out
+        if copy_out:
+            out = out.copy()
+        if copy_lp:
+            lp = lp.copy()
+        return out if lp is None else (out, lp)
+
+    def _result_buffer(self, what: str, N: int) -> np.ndarray:
+        cache = self.__dict__.setdefault("_result_cache", {})
+        buf = cache.get(what)
+        if buf is None or buf.shape[0] < N:
+            buf = cache[what] = np.empty((max(N, 64), 21), dtype=np.float32)
+        return buf[:N]
+
+    def set_graphs(self, on: bool):
+        self._check(self._lib.tmpnn_set_graphs(self._ctx, int(on)))
+
+    def graph_launch_count(self) -> int:
+        return int(self._lib.tmpnn_graph_launch_count(self._ctx))
 
     # ---- introspection ----------------------------------------------------
     _SHAPES = {"E_idx": ((48,), np.int32), "D_nb": ((48,), np.float32), "h_E": ((48, 128), np.float32),
-               "h_V": ((128,), np.float32), "dec1": ((128,), np.float32), "dec2": ((128,), np.float32),
-               "table": ((21,), np.float32)}
+               "h_V": ((128,), np.float32), "dec0": ((128,), np.float32), "dec1": ((128,), np.float32),
+               "dec2": ((128,), np.float32), "table": ((21,), np.float32), "log_probs": ((21,), np.float32)}
 
     def fetch(self, name: str) -> np.ndarray:
         shape, dt = self._SHAPES[name]

@@ -1,7 +1,9 @@
 """PDB text -> the dict schema the model consumes.
 
-Behaviour-compatible with the reference's ``alt_parse_PDB`` / ``alt_parse_PDB_biounits``
-(protein_mpnn_utils.py:183-350), re-implemented as one vectorisable pass over the file:
+Behaviour-compatible with the reference's ``alt_parse_PDB`` / ``parse_PDB`` and their ``*_biounits`` helpers
+(protein_mpnn_utils.py:26-180, 183-350), re-implemented as ONE pass over the file (the reference re-reads and
+re-scans the whole file once per candidate chain letter: 352 scans with the default chain list) with the per-record
+work vectorised in numpy (fixed-column slicing of all ATOM records at once, float parsing in C):
 
 * only ``ATOM`` records, plus ``HETATM`` MSE rewritten to MET (:218-220);
 * chain = column 22; atom name = cols 13-16 stripped; residue field = cols 23-27 (number + optional insertion
@@ -10,8 +12,10 @@ Behaviour-compatible with the reference's ``alt_parse_PDB`` / ``alt_parse_PDB_bi
 * every integer residue number between the chain's min and max is emitted; missing ones become '-' with NaN
   coordinates (:256-276); insertion codes are emitted in sorted order after their residue number;
 * unknown 3-letter codes map to '-' in ``seq`` while their coordinates are kept (:261);
-* ``name`` = file basename minus its last 4 characters (:340-341); ``resn_list`` keeps the residue labels of the
-  last chain parsed (:346).
+* ``name`` = file basename minus its last 4 characters (:340-341);
+* ``resn_list`` (``alt_parse_PDB`` only) is what the LAST chain letter iterated returned (:346): that chain's residue
+  labels in order of first appearance, or -- when that letter is not in the file, e.g. with the default chain list --
+  ``list('no_chain')``, exactly as upstream.
 """
 from __future__ import annotations
 
@@ -23,76 +27,124 @@ import numpy as np
 _AA3 = ['ALA', 'ARG', 'ASN', 'ASP', 'CYS', 'GLN', 'GLU', 'GLY', 'HIS', 'ILE',
         'LEU', 'LYS', 'MET', 'PHE', 'PRO', 'SER', 'THR', 'TRP', 'TYR', 'VAL']
 _AA1 = "ARNDCQEGHILKMFPSTWYV"
-_THREE_TO_ONE = dict(zip(_AA3, _AA1))
-_BACKBONE = ("N", "CA", "C", "O")
+_THREE_TO_ONE = {a.encode(): b for a, b in zip(_AA3, _AA1)}
+_BACKBONE = (b"N", b"CA", b"C", b"O")
+_BACKBONE_NAMES = ("N", "CA", "C", "O")
 _DEFAULT_CHAINS = [chr(c) for c in range(ord('A'), ord('Z') + 1)] + [chr(c) for c in range(ord('a'), ord('z') + 1)] + \
                   [str(i) for i in range(300)]
+_W = 54   # columns needed: up to the z coordinate
 
 
-def _parse_chain(lines: List[str], chain: str):
-    """One chain -> (xyz [L,4,3] float64 with NaN for missing, seq str, residue labels) or None if absent."""
-    xyz: Dict[int, Dict[str, Dict[str, np.ndarray]]] = {}
-    seq: Dict[int, Dict[str, str]] = {}
-    labels: List[str] = []
-    seen = set()
-    lo, hi = None, None
-    for line in lines:
-        if line[:6] == "HETATM" and line[17:20] == "MSE":
-            line = line.replace("HETATM", "ATOM  ").replace("MSE", "MET")
-        if line[:4] != "ATOM" or line[21:22] != chain:
+class _Records:
+    """All ATOM records of a file as column arrays (one pass over the text)."""
+
+    def __init__(self, path: str):
+        with open(path, "rb") as f:
+            data = f.read()
+        rows = []
+        for ln in data.split(b"\n"):
+            if ln[:4] == b"ATOM":
+                pass
+            elif ln[:6] == b"HETATM" and ln[17:20] == b"MSE":
+                ln = ln.replace(b"HETATM", b"ATOM  ").replace(b"MSE", b"MET")
+            else:
+                continue
+            if not ln.isascii():                                     # upstream decodes with errors='ignore'
+                ln = ln.decode("utf-8", "ignore").encode("utf-8", "ignore")
+            ln = ln.rstrip()
+            rows.append(ln[:_W].ljust(_W))
+        self.n = len(rows)
+        if not rows:
+            return
+        a = np.frombuffer(b"".join(rows), dtype=np.uint8).reshape(self.n, _W)
+        self.chain = a[:, 21].copy()
+        self.atom = np.char.strip(np.ascontiguousarray(a[:, 12:16]).view("S4").ravel())
+        self.resi = np.ascontiguousarray(a[:, 17:20]).view("S3").ravel()
+        self.label = np.char.strip(np.ascontiguousarray(a[:, 22:27]).view("S5").ravel())
+        xyz = np.ascontiguousarray(a[:, 30:54]).view("S8").reshape(self.n, 3)
+        self.xyz = xyz.astype(np.float64)                            # same correctly-rounded parse as float(str)
+
+    def chain_rows(self, ch: str) -> np.ndarray:
+        if self.n == 0 or len(ch) != 1:                              # the reference compares line[21:22] == chain
+            return np.zeros(0, dtype=np.int64)
+        return np.nonzero(self.chain == ord(ch))[0]
+
+
+def _build_chain(rec: _Records, rows: np.ndarray):
+    """One chain -> (xyz [L,4,3] float64 with NaN for missing, seq str, residue labels in order of first appearance)."""
+    labels = rec.label[rows]
+    # residue key = (number - 1, insertion letter or '')
+    last = np.asarray([l[-1:] for l in labels.tolist()], dtype="S1")
+    has_ins = np.char.isalpha(last)
+    num = np.asarray([int(l[:-1]) if h else int(l) for l, h in zip(labels.tolist(), has_ins.tolist())], dtype=np.int64) - 1
+    ins = np.where(has_ins, last, b"")
+    lo, hi = int(num.min()), int(num.max())
+    # residues present, ordered by (number, insertion code) with '' first -- sorted(dict) upstream
+    key = np.rec.fromarrays([num, ins], names="num,ins")
+    ukey, first, inv = np.unique(key, return_index=True, return_inverse=True)
+    n_res_present = len(ukey)
+    # output row of each present residue: gaps (missing numbers) take one row each
+    present_nums = np.unique(num)
+    is_present = np.zeros(hi - lo + 1, dtype=bool)
+    is_present[present_nums - lo] = True
+    per_num = np.ones(hi - lo + 1, dtype=np.int64)                   # a missing number emits one '-' row
+    cnt = np.bincount(ukey.num - lo, minlength=hi - lo + 1)
+    per_num[is_present] = cnt[is_present]
+    start_of_num = np.concatenate([[0], np.cumsum(per_num)[:-1]])
+    L = int(per_num.sum())
+    rank_in_num = np.arange(n_res_present) - np.searchsorted(ukey.num, ukey.num, side="left")
+    out_row = start_of_num[ukey.num - lo] + rank_in_num              # [n_res_present]
+    seq = np.full(L, "-", dtype="U1")
+    resi_first = rec.resi[rows][first]
+    seq[out_row] = [_THREE_TO_ONE.get(r, "-") for r in resi_first.tolist()]
+    xyz = np.full((L, 4, 3), np.nan, dtype=np.float64)
+    atoms = rec.atom[rows]
+    coords = rec.xyz[rows]
+    for ai, name in enumerate(_BACKBONE):
+        sel = np.nonzero(atoms == name)[0]
+        if sel.size == 0:
             continue
-        label = line[22:27].strip()
-        if label not in seen:
-            seen.add(label)
-            labels.append(label)
-        if label[-1].isalpha():
-            ins, num = label[-1], int(label[:-1]) - 1
-        else:
-            ins, num = "", int(label) - 1
-        lo = num if lo is None or num < lo else lo
-        hi = num if hi is None or num > hi else hi
-        seq.setdefault(num, {}).setdefault(ins, line[17:20])
-        atoms = xyz.setdefault(num, {}).setdefault(ins, {})
-        name = line[12:16].strip()
-        if name not in atoms:
-            atoms[name] = np.array([float(line[30:38]), float(line[38:46]), float(line[46:54])])
-    if lo is None:
-        return None
-    out_seq, out_xyz = [], []
-    nan3 = np.full(3, np.nan)
-    for num in range(lo, hi + 1):
-        if num in seq:
-            for ins in sorted(seq[num]):
-                out_seq.append(_THREE_TO_ONE.get(seq[num][ins], "-"))
-        else:
-            out_seq.append("-")
-        if num in xyz:
-            for ins in sorted(xyz[num]):
-                out_xyz.append([xyz[num][ins].get(a, nan3) for a in _BACKBONE])
-        else:
-            out_xyz.append([nan3] * 4)
-    return np.asarray(out_xyz, dtype=np.float64).reshape(-1, 4, 3), "".join(out_seq), labels
+        res_of = inv.ravel()[sel]
+        # first occurrence of this atom in each residue wins
+        _, f = np.unique(res_of, return_index=True)
+        xyz[out_row[res_of[f]], ai] = coords[sel[f]]
+    _, order = np.unique(labels, return_index=True)
+    resn_list = [l.decode() for l in labels[np.sort(order)].tolist()]
+    return xyz, "".join(seq.tolist()), resn_list
+
+
+def _parse(path_to_pdb: str, input_chain_list: Optional[Sequence[str]], with_resn: bool) -> List[dict]:
+    rec = _Records(path_to_pdb)
+    chains = input_chain_list if input_chain_list else _DEFAULT_CHAINS
+    d: dict = {"resn_list": []} if with_resn else {}
+    concat, n_chains = "", 0
+    resn_list: List[str] = list("no_chain")
+    for ch in chains:
+        rows = rec.chain_rows(ch)
+        if rows.size == 0:
+            resn_list = list("no_chain")                              # what upstream's helper returns for a missing chain
+            continue
+        xyz, seq, resn_list = _build_chain(rec, rows)
+        concat += seq
+        d["seq_chain_" + ch] = seq
+        d["coords_chain_" + ch] = {f"{a}_chain_{ch}": xyz[:, i, :].tolist() for i, a in enumerate(_BACKBONE_NAMES)}
+        n_chains += 1
+    fi = path_to_pdb.rfind("/")
+    d["name"] = path_to_pdb[fi + 1:-4]
+    d["num_of_chains"] = n_chains
+    d["seq"] = concat
+    if with_resn:
+        d["resn_list"] = list(resn_list)
+    return [d]
 
 
 def alt_parse_PDB(path_to_pdb: str, input_chain_list: Optional[Sequence[str]] = None) -> List[dict]:
     """Same call and return shape as the reference's ``alt_parse_PDB(path, chains)`` (backbone atoms only).
     ``input_chain_list`` is iterated element-wise, so a string like ``"AB"`` means chains A and B (as upstream)."""
-    with open(path_to_pdb, "rb") as f:
-        lines = [ln.decode("utf-8", "ignore").rstrip() for ln in f]
-    chains = input_chain_list if input_chain_list else _DEFAULT_CHAINS
-    d: dict = {}
-    concat, n_chains, labels = "", 0, []
-    for ch in chains:
-        parsed = _parse_chain(lines, ch)
-        if parsed is None:
-            continue
-        xyz, seq, labels = parsed
-        concat += seq
-        d["seq_chain_" + ch] = seq
-        d["coords_chain_" + ch] = {f"{a}_chain_{ch}": xyz[:, i, :].tolist() for i, a in enumerate(_BACKBONE)}
-        n_chains += 1
-    d["name"] = os.path.basename(path_to_pdb)[:-4]
-    d["num_of_chains"] = n_chains
-    d["seq"] = concat
-    d["resn_list"] = list(labels)
-    return [d]
+    return _parse(path_to_pdb, input_chain_list, with_resn=True)
+
+
+def parse_PDB(path_to_pdb: str, input_chain_list: Optional[Sequence[str]] = None) -> List[dict]:
+    """The reference's ``parse_PDB`` (protein_mpnn_utils.py:126-180), which the Megascale / FireProt dataset classes
+    use (datasets.py:19-21): the same dict without ``resn_list``."""
+    return _parse(path_to_pdb, input_chain_list, with_resn=False)

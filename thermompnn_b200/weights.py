@@ -54,12 +54,12 @@ def load_state(path: str, vanilla_path: Optional[str] = None) -> Dict[str, np.nd
     return state
 
 
-def random_state(seed: int = 0) -> Dict[str, np.ndarray]:
-    """Random-init weights of the same architecture (for benchmarks when no checkpoint is at hand)."""
+def random_state(seed: int = 0, cfg=None) -> Dict[str, np.ndarray]:
+    """Random-init weights of the architecture ``cfg`` describes (``engine.ModelCfg``; default = the shipped model)."""
     from .engine import weight_table
     rng = np.random.default_rng(seed)
     state = {}
-    for name, _, r, c in weight_table():
+    for name, _, r, c in weight_table(cfg):
         if "norm" in name and name.endswith(".weight"):
             v = np.ones((r, c))
         elif name.endswith(".bias"):
