@@ -68,6 +68,8 @@ struct LogProbArgs {
 cudaError_t kernels_init();
 cudaError_t head_kernels_init();
 cudaError_t node_kernels_init();
+cudaError_t node_mma_kernels_init();
+void launch_node_update_mma(const NodeUpdArgs& a, cudaStream_t st);   // warp-level tensor-core cluster form (node_mma_kernels.cu)
 cudaError_t tc_kernels_init();
 cudaError_t tc_take_error();   // sticky host-side error of the tensor-core launchers (tensor-map encoding), cleared on read
 int knn_max_len();

@@ -730,6 +730,7 @@ template <int NT> static size_t smem_head() {
 
 cudaError_t node_kernels_init() {
     cudaError_t e;
+    if ((e = node_mma_kernels_init()) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(node_update_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_node_update<8>())) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(node_update_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_node_update<16>())) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(node_update_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_node_update<12>())) != cudaSuccess) return e;
@@ -742,11 +743,16 @@ cudaError_t node_kernels_init() {
     return cudaSuccess;
 }
 
+constexpr int NODE_MMA_MAX = 593;    // residues: up to here the clusters (one 16-residue tile each, 4 CTAs) fit in ONE wave on 148 SMs
+
 void launch_node_update(const NodeUpdArgs& a, int sms, cudaStream_t st) {
     // Small batches: a 4-CTA cluster per tile of NT residues, NT chosen so that the whole grid is ONE wave (152 CTAs on
     // 148 SMs would take two).  Large batches: the single-CTA step kernel, 16 or 32 residues per block.
     // All forms are bit-identical per residue, so the choice never shows in the results.
     const int N = a.N;
+    // Small and medium batches: the warp-level tensor-core cluster form (node_mma_kernels.cu), one 16-residue tile per
+    // 4-CTA cluster.  (The FP32 forms below remain for larger batches and for the dev build's SIMT message kernels.)
+    if (a.Spart && N < NODE_MMA_MAX) { launch_node_update_mma(a, st); return; }
     if (4 * ((N + 7) / 8) <= sms) {
         launch_pdl(node_update_kernel<8>, dim3(4 * ((N + 7) / 8)), dim3(NC_THREADS), smem_node_update<8>(), st, a);
     } else if (4 * ((N + 11) / 12) <= sms) {

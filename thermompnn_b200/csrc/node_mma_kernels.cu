@@ -1,0 +1,310 @@
+// node_update for small and medium batches: warp-level tensor-core form (mma.sync m16n8k8, 3xTF32) inside a 4-CTA cluster.
+//
+//   dh = (W3.Ssum + cnt*b3)/30 ; h = LN1(h_V + dh) ; h = LN2(h + FFN(h)) ; h *= mask          protein_mpnn_utils.py:826-832, 871-880
+//   then the per-residue projections the next edge kernels gather (W1a.h, W1c.h, W11a.h, W11c.h; engine.cu).
+//
+// Why this form: for one 300-residue protein (the headline configuration) node_update is a LATENCY chain, six times per
+// call -- 19 clusters, each a dependent sequence W3 -> LN -> FFN-in -> FFN-out -> LN -> projections over 0.8 MB of
+// weights.  The FP32 SIMT cluster kernel spent 10 of its 17 us in the four GEMM phases (clock64 trace,
+// profiles/r02_node_trace.md); on the warp-level tensor cores each phase is 12-48 mma instructions per warp.
+//
+// A cluster of four CTAs owns a tile of 16 residues = one m16 MMA tile.  CTA q loads only its quarter of the weights
+// (requested up front, before the dependency wait) and keeps it resident:
+//   W3      K-split   CTA q: input columns [32q, 32q+32)            -> partial [16][128]  -> cluster all-reduce (DSMEM)
+//   W_in    N-split   CTA q: hidden block q (columns [128q, 128q+128))                     -> stays local ...
+//   W_out   K-split   CTA q: rows [128q, 128q+128) = exactly the hidden block it produced  -> partial -> all-reduce
+//   proj    N-split   CTA q: projection q
+// The all-reduces add the four partials in rank order, so the result does not depend on timing; a residue's result does
+// not depend on what else is in the batch (every (row, column) runs the same instruction sequence wherever its tile sits).
+//
+// Inside a CTA: 16 warps, warp w owns output columns [8w, 8w+8) (one n8 block); lane (g = lane/4, t = lane%4) holds
+// rows {g, g+8} x columns {8w+2t, 8w+2t+1} of every [16][128] result (the m16n8 accumulator layout).
+// 3xTF32: x = hi + lo with hi = x & 0xffffe000 (exactly what the tensor core reads of x) and lo = x - hi (exact);
+// D = A_lo.B_hi + A_hi.B_lo (small terms, own accumulator) + A_hi.B_hi, fp32 accumulation; dropped lo.lo <= 2^-20.
+// Weight chunks ([32 k][128 n] fp32, 16 KB) sit in shared memory with their 16-byte granules XOR-swizzled by (k & 3) so
+// that a B-fragment load (rows k0+t, columns 8w+g) is bank-conflict free.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "pdl.cuh"
+
+namespace tmpnn {
+
+namespace {
+
+constexpr int NM_THREADS = 512;
+constexpr int NM_SLOTS = 9;          // resident weight chunks: W3 | W_in x4 | W_out x4; the projections reuse slots 1..4
+constexpr int NM_T = 16;             // residues per cluster tile
+constexpr int NM_P = HID + 4;        // row pitch of activation tiles: rows g -> banks 4g + t, conflict-free A-fragment loads
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split3(float x, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+// acc_m / acc_c += A[16][32 k] . W[32 k][n-block of this warp]   (one weight chunk: four k8 steps)
+//   A: activation tile in shared memory, row pitch NM_P, k offset already applied;  W: swizzled chunk.
+__device__ __forceinline__ void mma_chunk(float (&acc_m)[4], float (&acc_c)[4], const float* __restrict__ A,
+                                          const float* __restrict__ W, int g, int t, int ncol) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        const int k0 = 8 * ks;
+        uint32_t ah[4], al[4], bh[2], bl[2];
+        split3(A[g * NM_P + k0 + t], ah[0], al[0]);
+        split3(A[(g + 8) * NM_P + k0 + t], ah[1], al[1]);
+        split3(A[g * NM_P + k0 + t + 4], ah[2], al[2]);
+        split3(A[(g + 8) * NM_P + k0 + t + 4], ah[3], al[3]);
+        const int col = ncol ^ (t << 3);                    // (k & 3) == t for both rows below
+        split3(W[(k0 + t) * HID + col], bh[0], bl[0]);
+        split3(W[(k0 + t + 4) * HID + col], bh[1], bl[1]);
+        mma_tf32(acc_c, al, bh[0], bh[1]);
+        mma_tf32(acc_c, ah, bl[0], bl[1]);
+        mma_tf32(acc_m, ah, bh[0], bh[1]);
+    }
+}
+
+}  // namespace
+
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NM_THREADS, 1) node_update_mma_kernel(NodeUpdArgs a) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int q = (int)cluster.block_rank();
+    extern __shared__ __align__(16) float smem[];
+    float* ring = smem;                              // [NM_SLOTS][4096]
+    float* x = ring + NM_SLOTS * WCHUNK_FLOATS;      // [16][NM_P]  neighbour sum, then LN1 output, then the final h
+    float* hid = x + NM_T * NM_P;                    // [16][NM_P]  this CTA's block of the FFN hidden layer
+    float* xr0 = hid + NM_T * NM_P;                  // [16][128]   this CTA's partials, read by the other three CTAs
+    float* xr1 = xr0 + NM_T * HID;                   //             (one buffer per all-reduce: no second cluster barrier)
+    float* red = xr1 + NM_T * HID;                   // [16 warps][16 rows]
+    float* cnt_s = red + 16 * NM_T;                  // [16]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int ncol = 8 * warp + g;                   // B-fragment column of this lane
+    const int c0 = 8 * warp + 2 * t;                 // this lane's two output columns: c0, c0 + 1; rows g and g + 8
+    const int node0 = (blockIdx.x >> 2) * NM_T;
+    const float* wb = a.weights;
+#define NM_STAMP(i_) do { if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[i_] = clock64(); } while (0)
+    NM_STAMP(0);
+
+    const bool has_proj = a.nproj > 0 && q < a.nproj;
+    auto issue = [&](int k, int slot) {                // chunk k of this CTA -> slot (swizzled); always one commit group
+        const float* src = wb + a.w.stream + (size_t)(4 * k + q) * WCHUNK_FLOATS;
+        float* dst = ring + slot * WCHUNK_FLOATS;
+#pragma unroll
+        for (int i = 0; i < WCHUNK_FLOATS / 4 / NM_THREADS; ++i) {
+            const int gi = threadIdx.x + i * NM_THREADS;               // granule index: row kk = gi / 32, granule gn = gi % 32
+            const int kk = gi >> 5, gn = gi & 31;
+            cp_async16(dst + kk * HID + ((gn ^ ((kk & 3) << 1)) << 2), src + gi * 4);
+        }
+        cp_async_commit();
+    };
+    pdl_trigger();
+#pragma unroll
+    for (int k = 0; k < NM_SLOTS; ++k) issue(k, k);
+    NM_STAMP(1);
+    pdl_wait();                                      // everything below reads earlier kernels' output
+    NM_STAMP(2);
+
+    // ---- inputs: neighbour sums (three 16-row partials per residue, added in order), edge-weight counts, h_V
+    for (int i = threadIdx.x; i < NM_T * (HID / 4); i += NM_THREADS) {
+        const int r = i / (HID / 4), c4 = (i % (HID / 4)) * 4, node = node0 + r;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (node < a.N) {
+            const float* sp = a.Spart + (size_t)node * 3 * HID + c4;
+            const float4 p0 = *reinterpret_cast<const float4*>(sp), p1 = *reinterpret_cast<const float4*>(sp + HID),
+                         p2 = *reinterpret_cast<const float4*>(sp + 2 * HID);
+            s = make_float4((p0.x + p1.x) + p2.x, (p0.y + p1.y) + p2.y, (p0.z + p1.z) + p2.z, (p0.w + p1.w) + p2.w);
+        }
+        *reinterpret_cast<float4*>(x + r * NM_P + c4) = s;
+    }
+    {   // one warp per residue: sum of the edge weights (m_i m_j for the encoder, 1 for the decoder) over its used slots
+        const int node = node0 + warp;
+        float c = 0.f;
+        if (node < a.N) {
+            const float mi = a.maskf[node];
+            for (int k = lane; k < KNB; k += 32) {
+                const int j = a.E_idx[(size_t)node * KNB + k];
+                if (j >= 0) c += a.enc ? mi * a.maskf[j] : 1.0f;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane == 0) cnt_s[warp] = c;
+    }
+    float hv[4];                                     // h_V at (g, c0), (g, c0+1), (g+8, c0), (g+8, c0+1)
+    {
+        const int n0 = node0 + g, n1 = node0 + g + 8;
+        const float2 v0 = n0 < a.N ? *reinterpret_cast<const float2*>(a.hV + (size_t)n0 * HID + c0) : make_float2(0.f, 0.f);
+        const float2 v1 = n1 < a.N ? *reinterpret_cast<const float2*>(a.hV + (size_t)n1 * HID + c0) : make_float2(0.f, 0.f);
+        hv[0] = v0.x; hv[1] = v0.y; hv[2] = v1.x; hv[3] = v1.y;
+    }
+    // sum of the four CTAs' partials, in rank order
+    auto cluster_allreduce = [&](float (&v)[4], float* xr) {
+        *reinterpret_cast<float2*>(xr + g * HID + c0) = make_float2(v[0], v[1]);
+        *reinterpret_cast<float2*>(xr + (g + 8) * HID + c0) = make_float2(v[2], v[3]);
+        cluster.sync();
+        float2 p[4][2];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const float* rp = cluster.map_shared_rank(xr, r);
+            p[r][0] = *reinterpret_cast<const float2*>(rp + g * HID + c0);
+            p[r][1] = *reinterpret_cast<const float2*>(rp + (g + 8) * HID + c0);
+        }
+        v[0] = (p[0][0].x + p[1][0].x) + (p[2][0].x + p[3][0].x);
+        v[1] = (p[0][0].y + p[1][0].y) + (p[2][0].y + p[3][0].y);
+        v[2] = (p[0][1].x + p[1][1].x) + (p[2][1].x + p[3][1].x);
+        v[3] = (p[0][1].y + p[1][1].y) + (p[2][1].y + p[3][1].y);
+    };
+    // LayerNorm over the 128 columns of rows g and g + 8 (two-pass); block-wide barriers inside
+    auto layernorm = [&](float (&v)[4], const float* __restrict__ gam, const float* __restrict__ bet) {
+        float s0 = v[0] + v[1], s1 = v[2] + v[3];
+        s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+        if (t == 0) { red[warp * NM_T + g] = s0; red[warp * NM_T + g + 8] = s1; }
+        __syncthreads();
+        float m0 = 0.f, m1 = 0.f;
+#pragma unroll
+        for (int w = 0; w < 16; ++w) { m0 += red[w * NM_T + g]; m1 += red[w * NM_T + g + 8]; }
+        m0 *= (1.0f / HID); m1 *= (1.0f / HID);
+        __syncthreads();
+        const float d0 = v[0] - m0, d1 = v[1] - m0, d2 = v[2] - m1, d3 = v[3] - m1;
+        float q0 = fmaf(d0, d0, d1 * d1), q1 = fmaf(d2, d2, d3 * d3);
+        q0 += __shfl_xor_sync(0xffffffffu, q0, 1); q0 += __shfl_xor_sync(0xffffffffu, q0, 2);
+        q1 += __shfl_xor_sync(0xffffffffu, q1, 1); q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
+        if (t == 0) { red[warp * NM_T + g] = q0; red[warp * NM_T + g + 8] = q1; }
+        __syncthreads();
+        float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+        for (int w = 0; w < 16; ++w) { v0 += red[w * NM_T + g]; v1 += red[w * NM_T + g + 8]; }
+        const float r0 = 1.0f / sqrtf(v0 * (1.0f / HID) + LN_EPS), r1 = 1.0f / sqrtf(v1 * (1.0f / HID) + LN_EPS);
+        const float2 gg = __ldg(reinterpret_cast<const float2*>(gam + c0)), bb = __ldg(reinterpret_cast<const float2*>(bet + c0));
+        v[0] = d0 * r0 * gg.x + bb.x; v[1] = d1 * r0 * gg.y + bb.y;
+        v[2] = d2 * r1 * gg.x + bb.x; v[3] = d3 * r1 * gg.y + bb.y;
+        __syncthreads();                             // red may be reused
+    };
+    auto store_tile = [&](float* dst, const float (&v)[4]) {
+        *reinterpret_cast<float2*>(dst + g * NM_P + c0) = make_float2(v[0], v[1]);
+        *reinterpret_cast<float2*>(dst + (g + 8) * NM_P + c0) = make_float2(v[2], v[3]);
+    };
+
+    float am[4], ac[4], h[4];
+    NM_STAMP(3);
+    // ---- W3 (this CTA: input columns 32q..)
+    cp_async_wait<NM_SLOTS - 1>();                   // chunk 0
+    __syncthreads();                                 // ... of every thread; also publishes x / cnt_s
+#pragma unroll
+    for (int i = 0; i < 4; ++i) am[i] = ac[i] = 0.f;
+    mma_chunk(am, ac, x + 32 * q, ring, g, t, ncol);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) am[i] += ac[i];
+    NM_STAMP(4);
+    cluster_allreduce(am, xr0);
+    NM_STAMP(5);
+    {
+        const float2 b3 = __ldg(reinterpret_cast<const float2*>(wb + a.w.b3 + c0));
+        const float cg0 = cnt_s[g], cg1 = cnt_s[g + 8];
+        h[0] = hv[0] + fmaf(cg0, b3.x, am[0]) / MSG_SCALE; h[1] = hv[1] + fmaf(cg0, b3.y, am[1]) / MSG_SCALE;
+        h[2] = hv[2] + fmaf(cg1, b3.x, am[2]) / MSG_SCALE; h[3] = hv[3] + fmaf(cg1, b3.y, am[3]) / MSG_SCALE;
+    }
+    layernorm(h, wb + a.w.n1.g, wb + a.w.n1.b);      // ends with a barrier: x is free
+    NM_STAMP(6);
+    store_tile(x, h);
+    // ---- FFN 128 -> 512: this CTA's hidden block q
+    cp_async_wait<NM_SLOTS - 5>();                   // chunks 1..4
+    __syncthreads();                                 // + x
+#pragma unroll
+    for (int i = 0; i < 4; ++i) am[i] = ac[i] = 0.f;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) mma_chunk(am, ac, x + 32 * s, ring + (1 + s) * WCHUNK_FLOATS, g, t, ncol);
+    {
+        const float2 bi = __ldg(reinterpret_cast<const float2*>(wb + a.w.bin + q * HID + c0));
+        float v[4] = {gelu_erf(am[0] + ac[0] + bi.x), gelu_erf(am[1] + ac[1] + bi.y), gelu_erf(am[2] + ac[2] + bi.x),
+                      gelu_erf(am[3] + ac[3] + bi.y)};
+        store_tile(hid, v);
+    }
+    NM_STAMP(7);
+    // ---- FFN 512 -> 128: rows 128q.. = the block above
+    cp_async_wait<0>();                              // chunks 5..8
+    __syncthreads();                                 // + hid; slots 1..4 are free
+    if (has_proj)
+#pragma unroll
+        for (int s = 0; s < 4; ++s) issue(9 + s, 1 + s);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) am[i] = ac[i] = 0.f;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) mma_chunk(am, ac, hid + 32 * s, ring + (5 + s) * WCHUNK_FLOATS, g, t, ncol);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) am[i] += ac[i];
+    NM_STAMP(8);
+    cluster_allreduce(am, xr1);
+    NM_STAMP(9);
+    {
+        const float2 bo = __ldg(reinterpret_cast<const float2*>(wb + a.w.bout + c0));
+        h[0] += am[0] + bo.x; h[1] += am[1] + bo.y; h[2] += am[2] + bo.x; h[3] += am[3] + bo.y;
+    }
+    layernorm(h, wb + a.w.n2.g, wb + a.w.n2.b);
+    NM_STAMP(10);
+    {
+        const int n0 = node0 + g, n1 = node0 + g + 8;
+        const float m0 = n0 < a.N ? a.maskf[n0] : 0.f, m1 = n1 < a.N ? a.maskf[n1] : 0.f;
+        h[0] *= m0; h[1] *= m0; h[2] *= m1; h[3] *= m1;
+        store_tile(x, h);
+        if (q == 0) {
+            if (n0 < a.N) {
+                *reinterpret_cast<float2*>(a.hV + (size_t)n0 * HID + c0) = make_float2(h[0], h[1]);
+                if (a.hV_copy) *reinterpret_cast<float2*>(a.hV_copy + (size_t)n0 * HID + c0) = make_float2(h[0], h[1]);
+            }
+            if (n1 < a.N) {
+                *reinterpret_cast<float2*>(a.hV + (size_t)n1 * HID + c0) = make_float2(h[2], h[3]);
+                if (a.hV_copy) *reinterpret_cast<float2*>(a.hV_copy + (size_t)n1 * HID + c0) = make_float2(h[2], h[3]);
+            }
+        }
+    }
+    // ---- projections: CTA q computes projection q
+    if (has_proj) {
+        cp_async_wait<0>();
+        __syncthreads();                             // projection chunks + x
+#pragma unroll
+        for (int i = 0; i < 4; ++i) am[i] = ac[i] = 0.f;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) mma_chunk(am, ac, x + 32 * s, ring + (1 + s) * WCHUNK_FLOATS, g, t, ncol);
+        const ProjSpec ps = a.proj[q];
+        const float2 b = ps.bias >= 0 ? __ldg(reinterpret_cast<const float2*>(wb + ps.bias + c0)) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int node = node0 + g + 8 * half;
+            if (node < a.N) {
+                float2 v = make_float2(am[2 * half] + ac[2 * half] + b.x, am[2 * half + 1] + ac[2 * half + 1] + b.y);
+                if (ps.table >= 0) {
+                    const float2 tv = __ldg(reinterpret_cast<const float2*>(wb + ps.table + (size_t)a.S[node] * HID + c0));
+                    v.x += tv.x; v.y += tv.y;
+                }
+                *reinterpret_cast<float2*>(ps.out + (size_t)node * HID + c0) = v;
+            }
+        }
+    }
+    NM_STAMP(11);
+    cp_async_wait<0>();
+    cluster.sync();      // no CTA may exit while another can still read its shared memory
+    NM_STAMP(12);
+}
+
+static size_t smem_node_mma() {
+    return sizeof(float) * (NM_SLOTS * WCHUNK_FLOATS + 2 * NM_T * NM_P + 2 * NM_T * HID + 16 * NM_T + NM_T);
+}
+
+cudaError_t node_mma_kernels_init() {
+    return cudaFuncSetAttribute(node_update_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_node_mma());
+}
+
+void launch_node_update_mma(const NodeUpdArgs& a, cudaStream_t st) {
+    launch_pdl(node_update_mma_kernel, dim3(4 * ((a.N + NM_T - 1) / NM_T)), dim3(NM_THREADS), smem_node_mma(), st, a);
+}
+
+}  // namespace tmpnn

@@ -96,6 +96,31 @@ def synth_multichain(lengths: List[int], seed: int, name: Optional[str] = None) 
     return out
 
 
+_ONE_TO_THREE = dict(zip("ARNDCQEGHILKMFPSTWYV", ['ALA', 'ARG', 'ASN', 'ASP', 'CYS', 'GLN', 'GLU', 'GLY', 'HIS', 'ILE', 'LEU', 'LYS',
+                                                     'MET', 'PHE', 'PRO', 'SER', 'THR', 'TRP', 'TYR', 'VAL']))
+
+
+def write_pdb(pdb: dict, path: str, first_resnum: int = 1) -> None:
+    """Write a protein dict as PDB text (ATOM records of the backbone atoms; gap residues are skipped, so a parser
+    sees them as numbering gaps).  Round-trips through ``pdb.alt_parse_PDB`` / ``parse_PDB``."""
+    lines, serial = [], 1
+    for key in pdb:
+        if key[:10] != "seq_chain_":
+            continue
+        ch = key[-1:]
+        co = pdb[f"coords_chain_{ch}"]
+        for i, a in enumerate(pdb[key]):
+            if a == "-":
+                continue
+            for name in ("N", "CA", "C", "O"):
+                x, y, z = co[f"{name}_chain_{ch}"][i]
+                lines.append(f"ATOM  {serial:>5} {name:<4} {_ONE_TO_THREE[a]:>3} {ch}{first_resnum + i:>4}    {x:8.3f}{y:8.3f}{z:8.3f}  1.00  0.00")
+                serial += 1
+        lines.append("TER")
+    with open(path, "w") as f:
+        f.write("\n".join(lines) + "\nEND\n")
+
+
 # ---- the BASELINE.json workloads ------------------------------------------
 def config2() -> List[dict]:
     """C2: one 300-residue protein."""
@@ -116,3 +141,12 @@ def config5(n: int = 64, L: int = 2000) -> List[dict]:
 def megascale_like(names_and_seqs) -> List[dict]:
     """C4 shape: given (WT_name, aa_seq) pairs, synthetic coords seeded by crc32(name)."""
     return [synth(len(s), seed=zlib.crc32(n.encode()), seq=s, name=n) for n, s in names_and_seqs]
+
+
+def config4(shape_npz: str):
+    """C4: the Megascale-shaped batch (298 proteins, L 32..72) from the committed shape table (names, wild-type
+    sequences and the 271 231 listed single substitutions of the reference's mega_{train,val,test}.csv; made by
+    tools/make_golden_r2.py).  Returns (proteins, protein_index[int], position[int], mutant_letter_index[int])."""
+    d = np.load(shape_npz)
+    pdbs = megascale_like(zip([str(n) for n in d["names"]], [str(s) for s in d["seqs"]]))
+    return pdbs, d["protein"].astype(np.int64), d["position"].astype(np.int64), d["mutant"].astype(np.int64)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Dev tool: per-phase cycle breakdown of the tensor-core edge kernels (block 0), needs TMPNN_TC_TRACE=1."""
 import os, sys
-os.environ["TMPNN_TC_TRACE"] = "1"
+os.environ["TMPNN_TC_TRACE"] = "1"; os.environ["TMPNN_LIB"] = "dev"   # needs the -DTMPNN_DEV build (python __graft_entry__.py --dev)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import numpy as np
 from thermompnn_b200.featurize import featurize_batch

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Dev tool: single-tile timeline of the tensor-core edge kernels on workload C2 (one 300-residue protein), block 0."""
 import os, sys
-os.environ["TMPNN_TC_TRACE"] = "1"
+os.environ["TMPNN_TC_TRACE"] = "1"; os.environ["TMPNN_LIB"] = "dev"   # needs the -DTMPNN_DEV build (python __graft_entry__.py --dev)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 from thermompnn_b200.featurize import featurize_batch
 from thermompnn_b200.synth import synth
