@@ -97,7 +97,7 @@ struct tmpnn_ctx {
     cudaEvent_t stage_ev = nullptr;   // completion of the last H2D out of h_stage
     bool stage_busy = false;
     // per-node
-    DevBuf<float> atoms, maskf, hV, dec_first, dec_prev, dec_last, P, Q, P2, Q2, table, logp, Spart;
+    DevBuf<float> atoms, maskf, hV, dec_first, dec_prev, dec_last, P, Q, P2, Q2, table, logp, Spart, cnt_enc, cnt_dec;
     DevBuf<int> S_dev;                // S clamped to 0..20 by the first kernel
     // per-edge
     DevBuf<int> E_idx;
@@ -217,6 +217,19 @@ struct Prep {
                 if (q < (int)projs.size()) put_chunk(o, projs[q].first, 0, projs[q].second + 32 * s);
                 o += 4096;   // (alloc() zero-fills)
             }
+        // the same matrices as tensor-core images, in the order the tcgen05 form consumes them (tc_node_kernels.cu):
+        //   W3 | for q = 0..3: W_in rows [128q, +128) , W_out columns [128q, +128) | projections   (4 chunks of 32 KB each)
+        w.tc_chunks = 4 + 32 + 4 * (int)projs.size();
+        w.tc_stream = alloc((int64_t)w.tc_chunks * 8192);
+        {
+            int64_t t = w.tc_stream;
+            put_tc(t, p + "W3.weight", 0); t += 4 * 8192;
+            for (int q = 0; q < 4; ++q) {
+                put_tc(t, p + "dense.W_in.weight", 0, 4, HID * q); t += 4 * 8192;
+                put_tc(t, p + "dense.W_out.weight", HID * q); t += 4 * 8192;
+            }
+            for (auto& pr : projs) { put_tc(t, pr.first, pr.second); t += 4 * 8192; }
+        }
         w.b3 = vec(p + "W3.bias");
         w.n1 = ln(p + "norm1");
         w.n2 = ln(p + "norm2");
@@ -234,13 +247,13 @@ struct Prep {
         std::memcpy(&r, &u, 4);
         return r;
     }
-    void put_tc(int64_t off, const std::string& name, int col0, int nchunks = 4) {
+    void put_tc(int64_t off, const std::string& name, int col0, int nchunks = 4, int row0 = 0) {
         int out, in;
         const float* W = find(name, &out, &in);
         for (int c = 0; c < nchunks; ++c)
             for (int n = 0; n < HID; ++n)
                 for (int kk = 0; kk < 32; ++kk) {
-                    const float x = W[(int64_t)n * in + col0 + c * 32 + kk];
+                    const float x = W[(int64_t)(row0 + n) * in + col0 + c * 32 + kk];
                     const float hi = rna_tf32(x), lo = rna_tf32(x - hi);
                     const int64_t idx = off + (int64_t)c * 8192 + n * 32 + ((((kk >> 2) ^ (n & 7)) << 2) | (kk & 3));
                     dev[idx] = hi;
@@ -533,7 +546,7 @@ int enqueue_pipeline(tmpnn_ctx* ctx, const RunIO& io, cudaStream_t st) {
     CU(cudaMemsetAsync(ctx->hV.p, 0, n * HID * sizeof(float), st));
     { LaunchScope ls(ctx, st, "knn");
       launch_knn(io.off, B, io.X, io.m, io.S, N, io.lmax, ctx->atoms.p, ctx->maskf.p, ctx->S_dev.p, ctx->d_err, ctx->E_idx.p,
-                 ctx->D_nb.p, st); }
+                 ctx->D_nb.p, ctx->cnt_enc.p, ctx->cnt_dec.p, st); }
     if (!stage_done(1)) {
         if (tc_mask & 1) {
             LaunchScope ls(ctx, st, "tc_edge_feat");
@@ -570,7 +583,7 @@ int enqueue_pipeline(tmpnn_ctx* ctx, const RunIO& io, cudaStream_t st) {
             }
             NodeUpdArgs a{};
             a.weights = W; a.w = e.nu; a.hV = ctx->hV.p; a.hV_copy = nullptr;
-            a.Spart = ctx->Spart.p; a.E_idx = ctx->E_idx.p; a.enc = 1;
+            a.Spart = ctx->Spart.p; a.E_idx = ctx->E_idx.p; a.enc = 1; a.cnt_pre = ctx->cnt_enc.p; a.tc_img = e.nu.tc_stream;
 #ifdef TMPNN_DEV
             a.Ssum = ctx->Ssum.p; a.cnt = ctx->cnt.p;
             if (!(tc_mask & 2)) a.Spart = nullptr;
@@ -589,7 +602,7 @@ int enqueue_pipeline(tmpnn_ctx* ctx, const RunIO& io, cudaStream_t st) {
                 a.proj[3] = {-1, nx.Tseq, ctx->Q.p};
             }
             a.nproj = 4;
-            { LaunchScope ls(ctx, st, "node_update"); launch_node_update(a, ctx->sm_count, st); }
+            { LaunchScope ls(ctx, st, node_update_uses_tcgen05(N) && a.Spart ? "tc_node_update" : "node_update"); launch_node_update(a, ctx->sm_count, st); }
             if (tc_mask & 4) {
                 LaunchScope ls(ctx, st, "tc_edge_upd");
                 launch_tc_edge_upd(ctx->hE.p, ctx->E_idx.p, ctx->P2.p, ctx->Q2.p, ctx->maskf.p, W + e.tc_edge, W + e.b12, W + e.b13,
@@ -622,7 +635,7 @@ int enqueue_pipeline(tmpnn_ctx* ctx, const RunIO& io, cudaStream_t st) {
 #endif
             NodeUpdArgs a{};
             a.weights = W; a.w = d.nu; a.hV = ctx->hV.p;
-            a.Spart = ctx->Spart.p; a.E_idx = ctx->E_idx.p; a.enc = 0;
+            a.Spart = ctx->Spart.p; a.E_idx = ctx->E_idx.p; a.enc = 0; a.cnt_pre = ctx->cnt_dec.p; a.tc_img = d.nu.tc_stream;
 #ifdef TMPNN_DEV
             a.Ssum = ctx->Ssum.p; a.cnt = ctx->cnt.p;
             if (!(tc_mask & 2)) a.Spart = nullptr;
@@ -636,7 +649,7 @@ int enqueue_pipeline(tmpnn_ctx* ctx, const RunIO& io, cudaStream_t st) {
                 a.proj[1] = {-1, nx.Tseq, ctx->Q.p};
                 a.nproj = 2;
             }
-            { LaunchScope ls(ctx, st, "node_update"); launch_node_update(a, ctx->sm_count, st); }
+            { LaunchScope ls(ctx, st, node_update_uses_tcgen05(N) && a.Spart ? "tc_node_update" : "node_update"); launch_node_update(a, ctx->sm_count, st); }
             stage_done(6 + l);
         }
     }
@@ -764,6 +777,7 @@ int tmpnn_create(int device, tmpnn_ctx** out) {
     if ((e = node_kernels_init()) != cudaSuccess) return bail(std::string("node_kernels_init: ") + cudaGetErrorString(e));
     if ((e = tc_kernels_init()) != cudaSuccess) return bail(std::string("tc_kernels_init: ") + cudaGetErrorString(e));
     if ((e = head_kernels_init()) != cudaSuccess) return bail(std::string("head_kernels_init: ") + cudaGetErrorString(e));
+    if ((e = tc_node_kernels_init()) != cudaSuccess) return bail(std::string("tc_node_kernels_init: ") + cudaGetErrorString(e));
 #ifdef TMPNN_DEV
     if ((e = simt_kernels_init()) != cudaSuccess) return bail(std::string("simt_kernels_init: ") + cudaGetErrorString(e));
     if (const char* env = std::getenv("TMPNN_TC_TRACE"))
@@ -793,7 +807,7 @@ void tmpnn_destroy(tmpnn_ctx* ctx) {
     ctx->d_in.release();
     ctx->atoms.release(); ctx->maskf.release(); ctx->hV.release(); ctx->dec_first.release(); ctx->dec_prev.release();
     ctx->dec_last.release(); ctx->P.release(); ctx->Q.release(); ctx->P2.release(); ctx->Q2.release();
-    ctx->Spart.release(); ctx->S_dev.release(); ctx->logp.release();
+    ctx->Spart.release(); ctx->S_dev.release(); ctx->logp.release(); ctx->cnt_enc.release(); ctx->cnt_dec.release();
     ctx->table.release(); ctx->E_idx.release(); ctx->D_nb.release(); ctx->hE.release();
 #ifdef TMPNN_DEV
     ctx->Ssum.release(); ctx->cnt.release();
@@ -915,6 +929,7 @@ int tmpnn_run_batch_ex(tmpnn_ctx* ctx, int32_t B, const int32_t* offsets, const 
     // ---- buffers --------------------------------------------------------------
     const size_t n = (size_t)N, ne = n * KNB;
     CU(ctx->atoms.reserve(n * 16)); CU(ctx->maskf.reserve(n)); CU(ctx->S_dev.reserve(n));
+    CU(ctx->cnt_enc.reserve(n)); CU(ctx->cnt_dec.reserve(n));
     CU(ctx->hV.reserve(n * HID)); CU(ctx->dec_first.reserve(n * HID)); CU(ctx->dec_prev.reserve(n * HID));
     CU(ctx->dec_last.reserve(n * HID)); CU(ctx->Spart.reserve(n * 3 * HID));
     CU(ctx->P.reserve(n * HID)); CU(ctx->Q.reserve(n * HID)); CU(ctx->P2.reserve(n * HID)); CU(ctx->Q2.reserve(n * HID));

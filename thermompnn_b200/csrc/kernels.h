@@ -18,8 +18,10 @@ struct NodeUpdArgs {
     NodeUpdW w;
     const float* Ssum;   // [N][128] masked neighbour sum of the second GELU (SIMT message kernel), or
     const float* cnt;    // [N] sum of edge weights
-    const float* Spart;  // [N][3][128] per-32-row-block partial sums (tensor-core message kernel); then cnt is derived
-    const int* E_idx;    //   from E_idx / maskf here
+    const float* Spart;  // [N][3][128] per-16-row-block partial sums (tensor-core message kernel)
+    const float* cnt_pre; // [N] sum of the edge weights per residue, computed once per call by the knn kernel
+    const int* E_idx;    // (FP32 forms: cnt is re-derived from E_idx / maskf)
+    int64_t tc_img;      // tcgen05 form: weight images in the order that kernel consumes them (engine.cu: node_upd_tc)
     int enc;             //   1: edge weight m_i m_j (encoder)   0: weight 1 (decoder)
     float* hV;           // [N][128] in/out
     float* hV_copy;      // optional second destination (decoder states kept for the head)
@@ -70,6 +72,8 @@ cudaError_t head_kernels_init();
 cudaError_t node_kernels_init();
 cudaError_t node_mma_kernels_init();
 void launch_node_update_mma(const NodeUpdArgs& a, cudaStream_t st);   // warp-level tensor-core cluster form (node_mma_kernels.cu)
+cudaError_t tc_node_kernels_init();
+void launch_tc_node_update(const NodeUpdArgs& a, int sms, cudaStream_t st);   // tcgen05 form for large batches (tc_node_kernels.cu)
 cudaError_t tc_kernels_init();
 cudaError_t tc_take_error();   // sticky host-side error of the tensor-core launchers (tensor-map encoding), cleared on read
 int knn_max_len();
@@ -77,7 +81,7 @@ int knn_max_len();
 // first kernel of a call: per-residue atoms (N, CA, C, O, virtual C-beta) and float mask, then the k-NN graph
 // (also writes S_out = S clamped to 0..20 and raises *err_flag when it had to clamp)
 void launch_knn(const int* offsets, int B, const float* X, const uint8_t* mask, const int* S_in, int N, int lmax, float* atoms,
-                float* maskf, int* S_out, int* err_flag, int* E_idx, float* D_nb, cudaStream_t st);
+                float* maskf, int* S_out, int* err_flag, int* E_idx, float* D_nb, float* cnt_enc, float* cnt_dec, cudaStream_t st);
 void launch_head_generic(const HeadGenArgs& a, cudaStream_t st);
 void launch_log_probs(const LogProbArgs& a, cudaStream_t st);
 #ifdef TMPNN_DEV   // FP32 SIMT generation of the edge kernels (simt_edge_kernels.cu), bring-up only
@@ -102,6 +106,7 @@ void launch_tc_msg(bool dec, const float* hE, const int* E_idx, const float* P, 
                    const float* maskf, const float* wimg, const float* b2, float* Spart, int N, int sms, cudaStream_t st,
                    long long* trace = nullptr);
 void launch_node_update(const NodeUpdArgs& a, int sms, cudaStream_t st);
+bool node_update_uses_tcgen05(int N);   // which form launch_node_update picks for a batch of N residues
 void launch_head(const HeadArgs& a, int sms, cudaStream_t st);
 
 }  // namespace tmpnn

@@ -39,7 +39,8 @@ template <int NPL>
 __global__ void knn_kernel(const int* __restrict__ offsets, int B, const float* __restrict__ X,
                            const uint8_t* __restrict__ mask_u8, const int* __restrict__ S_in, int N, int lmax,
                            float* __restrict__ atoms, float* __restrict__ maskf, int* __restrict__ S_out,
-                           int* __restrict__ err_flag, int* __restrict__ E_idx, float* __restrict__ D_nb) {
+                           int* __restrict__ err_flag, int* __restrict__ E_idx, float* __restrict__ D_nb,
+                           float* __restrict__ cnt_enc, float* __restrict__ cnt_dec) {
     pdl_trigger();
     pdl_wait();
     extern __shared__ float s_row[];
@@ -205,6 +206,14 @@ __global__ void knn_kernel(const int* __restrict__ offsets, int B, const float* 
         E_idx[(size_t)i * KNB + r] = -1;
         D_nb[(size_t)i * KNB + r] = 0.f;
     }
+    // Sum of the edge weights of the residue, which every node update needs (b3 * sum_k w_ik): m_i m_j over the selected
+    // neighbours for the encoder (mask_attend, protein_mpnn_utils.py:1232-1233), the slot count for the decoder.
+    // (Sums of 0/1 values: exact in any order.)
+    float c = 0.f;
+    for (int e = lane; e < K; e += 32) c += mi * (mask_u8[s + seli[e]] ? 1.0f : 0.0f);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) { cnt_enc[i] = c; cnt_dec[i] = (float)K; }
 }
 
 cudaError_t kernels_init() {
@@ -213,17 +222,17 @@ cudaError_t kernels_init() {
 int knn_max_len() { return 200 * 1024 / 4 - 2 * KNB; }
 
 void launch_knn(const int* offsets, int B, const float* X, const uint8_t* mask, const int* S_in, int N, int lmax, float* atoms,
-                float* maskf, int* S_out, int* err_flag, int* E_idx, float* D_nb, cudaStream_t st) {
+                float* maskf, int* S_out, int* err_flag, int* E_idx, float* D_nb, float* cnt_enc, float* cnt_dec, cudaStream_t st) {
     int warps = 8;
     const int rowlen = lmax <= 512 ? 0 : lmax;            // register-resident rows up to 512 residues
     const size_t per_warp = (size_t)(rowlen + 2 * KNB) * 4;
     while (warps > 1 && (size_t)warps * per_warp > 200 * 1024) warps >>= 1;
     const size_t smem = (size_t)warps * per_warp;
     const dim3 grid((N + warps - 1) / warps), block(warps * 32);
-    if (lmax <= 128) launch_pdl(knn_kernel<4>, grid, block, smem, st, offsets, B, X, mask, S_in, N, lmax, atoms, maskf, S_out, err_flag, E_idx, D_nb);
-    else if (lmax <= 256) launch_pdl(knn_kernel<8>, grid, block, smem, st, offsets, B, X, mask, S_in, N, lmax, atoms, maskf, S_out, err_flag, E_idx, D_nb);
-    else if (lmax <= 512) launch_pdl(knn_kernel<16>, grid, block, smem, st, offsets, B, X, mask, S_in, N, lmax, atoms, maskf, S_out, err_flag, E_idx, D_nb);
-    else launch_pdl(knn_kernel<0>, grid, block, smem, st, offsets, B, X, mask, S_in, N, lmax, atoms, maskf, S_out, err_flag, E_idx, D_nb);
+    if (lmax <= 128) launch_pdl(knn_kernel<4>, grid, block, smem, st, offsets, B, X, mask, S_in, N, lmax, atoms, maskf, S_out, err_flag, E_idx, D_nb, cnt_enc, cnt_dec);
+    else if (lmax <= 256) launch_pdl(knn_kernel<8>, grid, block, smem, st, offsets, B, X, mask, S_in, N, lmax, atoms, maskf, S_out, err_flag, E_idx, D_nb, cnt_enc, cnt_dec);
+    else if (lmax <= 512) launch_pdl(knn_kernel<16>, grid, block, smem, st, offsets, B, X, mask, S_in, N, lmax, atoms, maskf, S_out, err_flag, E_idx, D_nb, cnt_enc, cnt_dec);
+    else launch_pdl(knn_kernel<0>, grid, block, smem, st, offsets, B, X, mask, S_in, N, lmax, atoms, maskf, S_out, err_flag, E_idx, D_nb, cnt_enc, cnt_dec);
 }
 
 }  // namespace tmpnn

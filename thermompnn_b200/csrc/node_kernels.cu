@@ -745,6 +745,8 @@ cudaError_t node_kernels_init() {
 
 constexpr int NODE_MMA_MAX = 593;    // residues: up to here the clusters (one 16-residue tile each, 4 CTAs) fit in ONE wave on 148 SMs
 
+bool node_update_uses_tcgen05(int N) { return N >= NODE_MMA_MAX; }
+
 void launch_node_update(const NodeUpdArgs& a, int sms, cudaStream_t st) {
     // Small batches: a 4-CTA cluster per tile of NT residues, NT chosen so that the whole grid is ONE wave (152 CTAs on
     // 148 SMs would take two).  Large batches: the single-CTA step kernel, 16 or 32 residues per block.
@@ -752,7 +754,9 @@ void launch_node_update(const NodeUpdArgs& a, int sms, cudaStream_t st) {
     const int N = a.N;
     // Small and medium batches: the warp-level tensor-core cluster form (node_mma_kernels.cu), one 16-residue tile per
     // 4-CTA cluster.  (The FP32 forms below remain for larger batches and for the dev build's SIMT message kernels.)
+    // Larger batches: the tcgen05 form (tc_node_kernels.cu), 128-residue tiles, persistent over the SMs.
     if (a.Spart && N < NODE_MMA_MAX) { launch_node_update_mma(a, st); return; }
+    if (a.Spart) { launch_tc_node_update(a, sms, st); return; }
     if (4 * ((N + 7) / 8) <= sms) {
         launch_pdl(node_update_kernel<8>, dim3(4 * ((N + 7) / 8)), dim3(NC_THREADS), smem_node_update<8>(), st, a);
     } else if (4 * ((N + 11) / 12) <= sms) {

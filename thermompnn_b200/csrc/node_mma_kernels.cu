@@ -123,20 +123,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NM_THREADS, 1) node_
         }
         *reinterpret_cast<float4*>(x + r * NM_P + c4) = s;
     }
-    {   // one warp per residue: sum of the edge weights (m_i m_j for the encoder, 1 for the decoder) over its used slots
-        const int node = node0 + warp;
-        float c = 0.f;
-        if (node < a.N) {
-            const float mi = a.maskf[node];
-            for (int k = lane; k < KNB; k += 32) {
-                const int j = a.E_idx[(size_t)node * KNB + k];
-                if (j >= 0) c += a.enc ? mi * a.maskf[j] : 1.0f;
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-        if (lane == 0) cnt_s[warp] = c;
-    }
+    if (threadIdx.x < NM_T) cnt_s[threadIdx.x] = (node0 + threadIdx.x < a.N) ? a.cnt_pre[node0 + threadIdx.x] : 0.f;
     float hv[4];                                     // h_V at (g, c0), (g, c0+1), (g+8, c0), (g+8, c0+1)
     {
         const int n0 = node0 + g, n1 = node0 + g + 8;

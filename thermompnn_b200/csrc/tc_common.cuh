@@ -240,5 +240,40 @@ __device__ __forceinline__ float gelu_fast(float x) {
     return fmaf(-0.5f * t, e, fmaxf(x, 0.f));     // relu(x) - (t/2) 2^P(t)
 }
 
+// ---- shared by the chained-GEMM kernels (tc_edge_kernels.cu, tc_node_kernels.cu) -------------------------------------------
+// TMEM columns: two fp32 accumulators and the hi / lo planes of the A operand, 128 columns each.
+constexpr uint32_t COL_D0 = 0, COL_D1 = 128, COL_AHI = 256, COL_ALO = 384;
+
+__device__ __forceinline__ void named_bar(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+
+// 16 values -> columns [16 sc, 16 sc + 16) of the next A operand (hi plane: the tf32 the tensor core would read anyway;
+// lo plane: the exact remainder, which the tensor core truncates to tf32 itself), then publish the sub-chunk.
+__device__ __forceinline__ void publish_A16(uint32_t lane_addr, int sc, const float (&v)[16], uint64_t* a_ready) {
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+        hi[j] = __float_as_uint(v[j]) & 0xffffe000u;
+        hi[j + 1] = __float_as_uint(v[j + 1]) & 0xffffe000u;
+        float l0, l1;                                   // lo = v - hi, exact (packed: fma(hi, -1, v))
+        upk2(fma2(pk2(__uint_as_float(hi[j]), __uint_as_float(hi[j + 1])), pk2(-1.0f, -1.0f), pk2(v[j], v[j + 1])), l0, l1);
+        lo[j] = __float_as_uint(l0);
+        lo[j + 1] = __float_as_uint(l1);
+    }
+    tmem_st16(lane_addr + COL_AHI + sc * 16, hi);
+    tmem_st16(lane_addr + COL_ALO + sc * 16, lo);
+    tmem_wait_st();
+    tc_fence_before();
+    mbar_arrive(a_ready);
+}
+__device__ __forceinline__ void load_vec16(float (&v)[16], const float* p) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float4 t = *reinterpret_cast<const float4*>(p + j * 4);
+        v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+    }
+}
+
+
 }  // namespace tc
 }  // namespace tmpnn

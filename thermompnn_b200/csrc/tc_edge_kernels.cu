@@ -28,7 +28,6 @@ namespace {
 constexpr int TC_ROWS = 128;
 constexpr int TC_WSLOTS = 3;
 constexpr uint32_t TC_WCHUNK_BYTES = 32768;   // [128 n][32 k] hi (16 KB) | lo (16 KB)
-constexpr uint32_t COL_D0 = 0, COL_D1 = 128, COL_AHI = 256, COL_ALO = 384;
 
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -134,27 +133,6 @@ __device__ __forceinline__ void halfwarp_colsum32(float (&v)[32], int lane) {
     }
 }
 
-__device__ __forceinline__ void named_bar(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
-
-// 16 values -> columns [16 sc, 16 sc + 16) of the next A operand (hi plane: the tf32 the tensor core would read anyway;
-// lo plane: the exact remainder, which the tensor core truncates to tf32 itself), then publish the sub-chunk.
-__device__ __forceinline__ void publish_A16(uint32_t lane_addr, int sc, const float (&v)[16], uint64_t* a_ready) {
-    uint32_t hi[16], lo[16];
-#pragma unroll
-    for (int j = 0; j < 16; j += 2) {
-        hi[j] = __float_as_uint(v[j]) & 0xffffe000u;
-        hi[j + 1] = __float_as_uint(v[j + 1]) & 0xffffe000u;
-        float l0, l1;                                   // lo = v - hi, exact (packed: fma(hi, -1, v))
-        upk2(fma2(pk2(__uint_as_float(hi[j]), __uint_as_float(hi[j + 1])), pk2(-1.0f, -1.0f), pk2(v[j], v[j + 1])), l0, l1);
-        lo[j] = __float_as_uint(l0);
-        lo[j + 1] = __float_as_uint(l1);
-    }
-    tmem_st16(lane_addr + COL_AHI + sc * 16, hi);
-    tmem_st16(lane_addr + COL_ALO + sc * 16, lo);
-    tmem_wait_st();
-    tc_fence_before();
-    mbar_arrive(a_ready);
-}
 // this thread's 16 floats (columns 16*half ..) of row r of an activation chunk
 __device__ __forceinline__ void load_act16(float (&v)[16], const float* chunk, int r, int half) {
 #pragma unroll
@@ -171,14 +149,6 @@ __device__ __forceinline__ void load_act16_sw(float (&v)[16], const float* chunk
         v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
     }
 }
-__device__ __forceinline__ void load_vec16(float (&v)[16], const float* p) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        float4 t = *reinterpret_cast<const float4*>(p + j * 4);
-        v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
-    }
-}
-
 // NSETS epilogue sets of four warps: set s handles the 16-column sub-chunks sc with sc % NSETS == s.
 // (Four sets -- 16 epilogue warps, two sub-chunks per thread and stage -- measured 8 % SLOWER than two: the epilogue is
 // bound by its instruction count, not by per-thread latency, and four sets publish their sub-chunks in two bursts,

@@ -122,6 +122,8 @@ struct LayerNormW { int64_t g, b; };
 struct NodeUpdW {           // what node_update needs for one Enc/Dec layer
     int64_t stream;         // KN chunks: W3 (4) | W_in column blocks 0..3 (4 each) | W_out (16) | projections (4 each)
     int32_t nchunks;
+    int64_t tc_stream;      // tensor-core images for the tcgen05 form: W3 | (W_in block q, W_out block q) x4 | projections
+    int32_t tc_chunks;
     int64_t b3, bin, bout;
     LayerNormW n1, n2;
 };
