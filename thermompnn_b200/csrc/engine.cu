@@ -121,12 +121,6 @@ struct tmpnn_ctx {
     cudaGraphExec_t graph_exec = nullptr;
     int64_t graph_launches = 0, graph_kernels = 0;
 
-#ifdef TMPNN_DEV
-    DevBuf<float> Ssum, cnt;          // SIMT message kernels' outputs
-    // TMPNN_TC=<mask> (bring-up / error localisation only): bit 0 edge_feat, 1 msg, 2 edge_upd; 0 selects the FP32 SIMT
-    // generation everywhere
-    int tc_mask = 7;
-#endif
     long long* d_trace = nullptr;     // -DTMPNN_DEV + TMPNN_TC_TRACE=1: phase stamps of enc layer 1's kernels
 
     bool profiling = false;
@@ -170,15 +164,6 @@ struct Prep {
         dev.resize(dev.size() + padded, 0.f);
         return off;
     }
-#ifdef TMPNN_DEV
-    // KN[k][n] = W[n][col0 + k] for a row-major nn.Linear weight W[out][in]
-    void put_kn(int64_t off, const std::string& name, int col0, int ncols) {
-        int out, in;
-        const float* W = find(name, &out, &in);
-        for (int k = 0; k < ncols; ++k)
-            for (int n = 0; n < out; ++n) dev[off + (int64_t)k * out + n] = W[(int64_t)n * in + col0 + k];
-    }
-#endif
     int64_t vec(const std::string& name) {
         int r, c;
         const float* v = find(name, &r, &c);
@@ -272,11 +257,6 @@ DevLayout prepare_weights(Prep& P, const tmpnn_model_cfg& cfg) {
         for (int q = 0; q < 66; ++q)
             for (int t = 0; t < 16; ++t) P.dev[L.pos_table + q * 16 + t] = W[t * 66 + q] + b[t];
     }
-#ifdef TMPNN_DEV
-    L.feat = P.alloc((int64_t)(EDGE_IN + HID) * HID);
-    P.put_kn(L.feat, pm + "features.edge_embedding.weight", 0, EDGE_IN);
-    P.put_kn(L.feat + (int64_t)EDGE_IN * HID, pm + "W_e.weight", 0, HID);
-#endif
     L.tc_feat = P.alloc(17 * 8192);
     P.put_tc(L.tc_feat, pm + "features.edge_embedding.weight", 0, 13);
     P.put_tc(L.tc_feat + 13 * 8192, pm + "W_e.weight", 0, 4);
@@ -292,15 +272,6 @@ DevLayout prepare_weights(Prep& P, const tmpnn_model_cfg& cfg) {
     for (int l = 0; l < 3; ++l) {
         const std::string p = pm + "encoder_layers." + std::to_string(l) + ".";
         EncW& e = L.enc[l];
-#ifdef TMPNN_DEV
-        e.msg = P.alloc(2 * HID * HID);
-        P.put_kn(e.msg, p + "W1.weight", HID, HID);
-        P.put_kn(e.msg + HID * HID, p + "W2.weight", 0, HID);
-        e.edge = P.alloc(3 * HID * HID);
-        P.put_kn(e.edge, p + "W11.weight", HID, HID);
-        P.put_kn(e.edge + HID * HID, p + "W12.weight", 0, HID);
-        P.put_kn(e.edge + 2 * HID * HID, p + "W13.weight", 0, HID);
-#endif
         e.tc_msg = P.alloc(8 * 8192);
         P.put_tc(e.tc_msg, p + "W1.weight", HID);
         P.put_tc(e.tc_msg + 4 * 8192, p + "W2.weight", 0);
@@ -332,11 +303,6 @@ DevLayout prepare_weights(Prep& P, const tmpnn_model_cfg& cfg) {
     for (int l = 0; l < 3; ++l) {
         const std::string p = pm + "decoder_layers." + std::to_string(l) + ".";
         DecW& d = L.dec[l];
-#ifdef TMPNN_DEV
-        d.msg = P.alloc(2 * HID * HID);
-        P.put_kn(d.msg, p + "W1.weight", HID, HID);
-        P.put_kn(d.msg + HID * HID, p + "W2.weight", 0, HID);
-#endif
         d.tc_msg = P.alloc(8 * 8192);
         P.put_tc(d.tc_msg, p + "W1.weight", HID);
         P.put_tc(d.tc_msg + 4 * 8192, p + "W2.weight", 0);
@@ -461,24 +427,6 @@ void drain_profile(tmpnn_ctx* c) {
 
 size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-#ifdef TMPNN_DEV
-// Residues per tile of the SIMT edge kernels: minimise (waves over the SMs) x (tile size).
-int choose_npt(int N, int sms) {
-    int best = 4;
-    double best_cost = 1e30;
-    for (int npt = 1; npt <= 4; ++npt) {
-        int tiles = (N + npt - 1) / npt;
-        int waves = (tiles + sms - 1) / sms;
-        double cost = (double)waves * (npt + 0.35);
-        if (cost < best_cost - 1e-9 || (std::fabs(cost - best_cost) < 1e-9 && npt > best)) {
-            best_cost = cost;
-            best = npt;
-        }
-    }
-    if (N >= 16 * sms) best = 4;
-    return best;
-}
-#endif
 
 const std::vector<RawTensor>& raw_table_default() {
     static const std::vector<RawTensor> t = build_raw_table(default_model_cfg());
@@ -534,12 +482,6 @@ int enqueue_pipeline(tmpnn_ctx* ctx, const RunIO& io, cudaStream_t st) {
     bool done = false;
     auto stage_done = [&](int s) { if (stop == s) done = true; return done; };
     const int* d_S = ctx->S_dev.p;
-#ifdef TMPNN_DEV
-    const int npt = choose_npt(N, ctx->sm_count);
-    const int tc_mask = ctx->tc_mask;
-#else
-    constexpr int tc_mask = 7;
-#endif
 
     // (h_V starts at zero, protein_mpnn_utils.py:1225; cleared up front so that no memset sits between two kernels
     // of the programmatic-dependent-launch chain)
@@ -548,18 +490,11 @@ int enqueue_pipeline(tmpnn_ctx* ctx, const RunIO& io, cudaStream_t st) {
       launch_knn(io.off, B, io.X, io.m, io.S, N, io.lmax, ctx->atoms.p, ctx->maskf.p, ctx->S_dev.p, ctx->d_err, ctx->E_idx.p,
                  ctx->D_nb.p, ctx->cnt_enc.p, ctx->cnt_dec.p, st); }
     if (!stage_done(1)) {
-        if (tc_mask & 1) {
+        {
             LaunchScope ls(ctx, st, "tc_edge_feat");
             launch_tc_edge_feat(ctx->atoms.p, ctx->E_idx.p, ctx->D_nb.p, io.r, io.c, W + L.pos_table, W + L.rbf_mu, W + L.tc_feat,
                                 W + L.ne.g, W + L.ne.b, W + L.be, ctx->hE.p, N, ctx->sm_count, st);
         }
-#ifdef TMPNN_DEV
-        else {
-            LaunchScope ls(ctx, st, "edge_feat");
-            launch_edge_feat(npt, ctx->atoms.p, ctx->E_idx.p, ctx->D_nb.p, io.r, io.c, W + L.pos_table, W + L.rbf_mu,
-                             W + L.feat, W + L.ne.g, W + L.ne.b, W + L.be, ctx->hE.p, N, st);
-        }
-#endif
     }
     if (!done && !stage_done(2)) {
         for (int l = 0; l < 3 && !done; ++l) {
@@ -568,26 +503,15 @@ int enqueue_pipeline(tmpnn_ctx* ctx, const RunIO& io, cudaStream_t st) {
                 const float* Pp = l == 0 ? W + e.b1 : ctx->P.p;
                 const float* Qp = l == 0 ? W + L.zeros : ctx->Q.p;
                 const int stride = l == 0 ? 0 : HID;
-                if (tc_mask & 2) {
+                {
                     LaunchScope ls(ctx, st, "tc_enc_msg");
                     launch_tc_msg(false, ctx->hE.p, ctx->E_idx.p, Pp, stride, Qp, stride, ctx->maskf.p, W + e.tc_msg, W + e.b2,
                                   ctx->Spart.p, N, ctx->sm_count, st, l == 1 ? ctx->d_trace : nullptr);
                 }
-#ifdef TMPNN_DEV
-                else {
-                    LaunchScope ls(ctx, st, "enc_msg");
-                    launch_msg(npt, false, ctx->hE.p, ctx->E_idx.p, Pp, stride, Qp, stride, ctx->maskf.p, W + e.msg, W + e.b2,
-                               ctx->Ssum.p, ctx->cnt.p, N, st);
-                }
-#endif
             }
             NodeUpdArgs a{};
             a.weights = W; a.w = e.nu; a.hV = ctx->hV.p; a.hV_copy = nullptr;
-            a.Spart = ctx->Spart.p; a.E_idx = ctx->E_idx.p; a.enc = 1; a.cnt_pre = ctx->cnt_enc.p; a.tc_img = e.nu.tc_stream;
-#ifdef TMPNN_DEV
-            a.Ssum = ctx->Ssum.p; a.cnt = ctx->cnt.p;
-            if (!(tc_mask & 2)) a.Spart = nullptr;
-#endif
+            a.Spart = ctx->Spart.p; a.cnt_pre = ctx->cnt_enc.p; a.tc_img = e.nu.tc_stream;
             a.maskf = ctx->maskf.p; a.S = d_S; a.N = N;
             a.trace = (l == 1 && ctx->d_trace) ? ctx->d_trace + 1024 : nullptr;
             a.proj[0] = {e.b11, -1, ctx->P2.p};     // edge update of this layer
@@ -602,44 +526,26 @@ int enqueue_pipeline(tmpnn_ctx* ctx, const RunIO& io, cudaStream_t st) {
                 a.proj[3] = {-1, nx.Tseq, ctx->Q.p};
             }
             a.nproj = 4;
-            { LaunchScope ls(ctx, st, node_update_uses_tcgen05(N) && a.Spart ? "tc_node_update" : "node_update"); launch_node_update(a, ctx->sm_count, st); }
-            if (tc_mask & 4) {
+            { LaunchScope ls(ctx, st, node_update_uses_tcgen05(N) ? "tc_node_update" : "node_update"); launch_node_update(a, ctx->sm_count, st); }
+            {
                 LaunchScope ls(ctx, st, "tc_edge_upd");
                 launch_tc_edge_upd(ctx->hE.p, ctx->E_idx.p, ctx->P2.p, ctx->Q2.p, ctx->maskf.p, W + e.tc_edge, W + e.b12, W + e.b13,
                                    W + e.n3.g, W + e.n3.b, N, ctx->sm_count, st, (l == 1 && ctx->d_trace) ? ctx->d_trace + 512 : nullptr);
             }
-#ifdef TMPNN_DEV
-            else {
-                LaunchScope ls(ctx, st, "edge_upd");
-                launch_edge_upd(npt, ctx->hE.p, ctx->E_idx.p, ctx->P2.p, ctx->Q2.p, W + e.edge, W + e.b12, W + e.b13,
-                                W + e.n3.g, W + e.n3.b, N, st);
-            }
-#endif
             stage_done(3 + l);
         }
     }
     if (!done) {
         for (int l = 0; l < 3 && !done; ++l) {
             const DecW& d = L.dec[l];
-            if (tc_mask & 2) {
+            {
                 LaunchScope ls(ctx, st, "tc_dec_msg");
                 launch_tc_msg(true, ctx->hE.p, ctx->E_idx.p, ctx->P.p, HID, ctx->Q.p, HID, ctx->maskf.p, W + d.tc_msg, W + d.b2,
                               ctx->Spart.p, N, ctx->sm_count, st);
             }
-#ifdef TMPNN_DEV
-            else {
-                LaunchScope ls(ctx, st, "dec_msg");
-                launch_msg(npt, true, ctx->hE.p, ctx->E_idx.p, ctx->P.p, HID, ctx->Q.p, HID, ctx->maskf.p, W + d.msg,
-                           W + d.b2, ctx->Ssum.p, ctx->cnt.p, N, st);
-            }
-#endif
             NodeUpdArgs a{};
             a.weights = W; a.w = d.nu; a.hV = ctx->hV.p;
-            a.Spart = ctx->Spart.p; a.E_idx = ctx->E_idx.p; a.enc = 0; a.cnt_pre = ctx->cnt_dec.p; a.tc_img = d.nu.tc_stream;
-#ifdef TMPNN_DEV
-            a.Ssum = ctx->Ssum.p; a.cnt = ctx->cnt.p;
-            if (!(tc_mask & 2)) a.Spart = nullptr;
-#endif
+            a.Spart = ctx->Spart.p; a.cnt_pre = ctx->cnt_dec.p; a.tc_img = d.nu.tc_stream;
             a.hV_copy = l == 0 ? ctx->dec_first.p : (l == 1 ? ctx->dec_prev.p : ctx->dec_last.p);
             a.maskf = ctx->maskf.p; a.S = d_S; a.N = N;
             a.nproj = 0;
@@ -649,7 +555,7 @@ int enqueue_pipeline(tmpnn_ctx* ctx, const RunIO& io, cudaStream_t st) {
                 a.proj[1] = {-1, nx.Tseq, ctx->Q.p};
                 a.nproj = 2;
             }
-            { LaunchScope ls(ctx, st, node_update_uses_tcgen05(N) && a.Spart ? "tc_node_update" : "node_update"); launch_node_update(a, ctx->sm_count, st); }
+            { LaunchScope ls(ctx, st, node_update_uses_tcgen05(N) ? "tc_node_update" : "node_update"); launch_node_update(a, ctx->sm_count, st); }
             stage_done(6 + l);
         }
     }
@@ -779,10 +685,8 @@ int tmpnn_create(int device, tmpnn_ctx** out) {
     if ((e = head_kernels_init()) != cudaSuccess) return bail(std::string("head_kernels_init: ") + cudaGetErrorString(e));
     if ((e = tc_node_kernels_init()) != cudaSuccess) return bail(std::string("tc_node_kernels_init: ") + cudaGetErrorString(e));
 #ifdef TMPNN_DEV
-    if ((e = simt_kernels_init()) != cudaSuccess) return bail(std::string("simt_kernels_init: ") + cudaGetErrorString(e));
     if (const char* env = std::getenv("TMPNN_TC_TRACE"))
         if (std::atoi(env)) { cudaMalloc(&ctx->d_trace, 3 * 512 * sizeof(long long)); cudaMemset(ctx->d_trace, 0, 3 * 512 * sizeof(long long)); }
-    if (const char* env = std::getenv("TMPNN_TC")) ctx->tc_mask = std::atoi(env) == 1 ? 7 : std::atoi(env);
 #endif
     if (const char* env = std::getenv("TMPNN_GRAPHS")) ctx->graphs = std::atoi(env) != 0;
     *out = ctx;
@@ -809,9 +713,6 @@ void tmpnn_destroy(tmpnn_ctx* ctx) {
     ctx->dec_last.release(); ctx->P.release(); ctx->Q.release(); ctx->P2.release(); ctx->Q2.release();
     ctx->Spart.release(); ctx->S_dev.release(); ctx->logp.release(); ctx->cnt_enc.release(); ctx->cnt_dec.release();
     ctx->table.release(); ctx->E_idx.release(); ctx->D_nb.release(); ctx->hE.release();
-#ifdef TMPNN_DEV
-    ctx->Ssum.release(); ctx->cnt.release();
-#endif
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -934,9 +835,6 @@ int tmpnn_run_batch_ex(tmpnn_ctx* ctx, int32_t B, const int32_t* offsets, const 
     CU(ctx->dec_last.reserve(n * HID)); CU(ctx->Spart.reserve(n * 3 * HID));
     CU(ctx->P.reserve(n * HID)); CU(ctx->Q.reserve(n * HID)); CU(ctx->P2.reserve(n * HID)); CU(ctx->Q2.reserve(n * HID));
     CU(ctx->E_idx.reserve(ne)); CU(ctx->D_nb.reserve(ne)); CU(ctx->hE.reserve(ne * HID));
-#ifdef TMPNN_DEV
-    CU(ctx->Ssum.reserve(n * HID)); CU(ctx->cnt.reserve(n));
-#endif
     io.table = out_table; io.logp = out_log_probs;
     if (!out_dev) {
         if (out_table) { CU(ctx->table.reserve(n * 21)); io.table = ctx->table.p; io.host_table = out_table; }

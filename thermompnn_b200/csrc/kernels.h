@@ -16,13 +16,9 @@ struct ProjSpec {      // out[i] = h_V[i] . W (+ bias) (+ table[S_i]); W is the 
 struct NodeUpdArgs {
     const float* weights;
     NodeUpdW w;
-    const float* Ssum;   // [N][128] masked neighbour sum of the second GELU (SIMT message kernel), or
-    const float* cnt;    // [N] sum of edge weights
     const float* Spart;  // [N][3][128] per-16-row-block partial sums (tensor-core message kernel)
     const float* cnt_pre; // [N] sum of the edge weights per residue, computed once per call by the knn kernel
-    const int* E_idx;    // (FP32 forms: cnt is re-derived from E_idx / maskf)
     int64_t tc_img;      // tcgen05 form: weight images in the order that kernel consumes them (engine.cu: node_upd_tc)
-    int enc;             //   1: edge weight m_i m_j (encoder)   0: weight 1 (decoder)
     float* hV;           // [N][128] in/out
     float* hV_copy;      // optional second destination (decoder states kept for the head)
     const float* maskf;  // [N]
@@ -84,18 +80,6 @@ void launch_knn(const int* offsets, int B, const float* X, const uint8_t* mask, 
                 float* maskf, int* S_out, int* err_flag, int* E_idx, float* D_nb, float* cnt_enc, float* cnt_dec, cudaStream_t st);
 void launch_head_generic(const HeadGenArgs& a, cudaStream_t st);
 void launch_log_probs(const LogProbArgs& a, cudaStream_t st);
-#ifdef TMPNN_DEV   // FP32 SIMT generation of the edge kernels (simt_edge_kernels.cu), bring-up only
-cudaError_t simt_kernels_init();
-void launch_edge_feat(int npt, const float* atoms, const int* E_idx, const float* D_nb, const int* ridx,
-                      const int* cenc, const float* pos_table, const float* rbf_mu, const float* wstream,
-                      const float* ln_g, const float* ln_b, const float* b_e, float* hE, int N, cudaStream_t st);
-void launch_msg(int npt, bool dec, const float* hE, const int* E_idx, const float* P, int p_stride, const float* Q,
-                int q_stride, const float* maskf, const float* wstream, const float* b2, float* Ssum, float* cnt,
-                int N, cudaStream_t st);
-void launch_edge_upd(int npt, float* hE, const int* E_idx, const float* P, const float* Q, const float* wstream,
-                     const float* b12, const float* b13, const float* ln_g, const float* ln_b, int N,
-                     cudaStream_t st);
-#endif
 void launch_tc_edge_upd(float* hE, const int* E_idx, const float* P, const float* Q, const float* maskf, const float* wimg,
                         const float* b12, const float* b13, const float* ln_g, const float* ln_b, int N, int sms, cudaStream_t st,
                         long long* trace = nullptr);

@@ -120,7 +120,7 @@ inline std::vector<RawTensor> build_raw_table(const tmpnn_model_cfg& cfg) {
 struct LayerNormW { int64_t g, b; };
 
 struct NodeUpdW {           // what node_update needs for one Enc/Dec layer
-    int64_t stream;         // KN chunks: W3 (4) | W_in column blocks 0..3 (4 each) | W_out (16) | projections (4 each)
+    int64_t stream;         // warp-level form: 16 KB [32 k][128 n] chunks, W3 (4) | W_in column blocks 0..3 (4 each) | W_out (16) | projections (4 each)
     int32_t nchunks;
     int64_t tc_stream;      // tensor-core images for the tcgen05 form: W3 | (W_in block q, W_out block q) x4 | projections
     int32_t tc_chunks;
@@ -129,19 +129,16 @@ struct NodeUpdW {           // what node_update needs for one Enc/Dec layer
 };
 
 struct EncW {
-    int64_t msg;            // [W1b | W2] KN, 8 chunks      (message kernel stream)
-    int64_t tc_msg;         // the same two matrices as tensor-core images (8 x 32 KB)
+    int64_t tc_msg;         // [W1b | W2] as tensor-core images (8 x 32 KB)
     int64_t b1, b2;
-    int64_t edge;           // [W11b | W12 | W13] KN, 12 chunks (edge-update stream)
-    int64_t tc_edge;        // same three matrices as tensor-core images: 12 x ([128 n][32 k] hi | lo), 128B-swizzled
+    int64_t tc_edge;        // [W11b | W12 | W13] as tensor-core images: 12 x ([128 n][32 k] hi | lo), 128B-swizzled
     int64_t b11, b12, b13;
     LayerNormW n3;
     NodeUpdW nu;
 };
 
 struct DecW {
-    int64_t msg;            // [W1b | W2] KN  (W1b = h_E block of the 512-wide W1)
-    int64_t tc_msg;
+    int64_t tc_msg;         // [W1b | W2] images  (W1b = h_E block of the 512-wide W1)
     int64_t b1, b2;
     int64_t Tseq;           // [21][128] = W_s . W1c^T : the h_S[j] term folded per letter
     NodeUpdW nu;
@@ -149,8 +146,7 @@ struct DecW {
 
 struct DevLayout {
     int64_t pos_table;      // [66][16]  = embeddings.linear.weight^T + bias
-    int64_t feat;           // [edge_embedding KN (416 rows) | W_e KN (128 rows)] 17 chunks
-    int64_t tc_feat;        // the same as tensor-core images: 13 + 4 chunks of 32 KB
+    int64_t tc_feat;        // [edge_embedding (416 in) | W_e] as tensor-core images: 13 + 4 chunks of 32 KB
     int64_t be;             // W_e bias
     LayerNormW ne;          // norm_edges
     int64_t rbf_mu;         // [16]

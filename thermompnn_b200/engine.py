@@ -12,7 +12,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# TMPNN_LIB=dev selects the development build (-DTMPNN_DEV: SIMT edge kernels, TMPNN_TC / TMPNN_PDL / TMPNN_TC_TRACE switches)
+# TMPNN_LIB=dev selects the development build (-DTMPNN_DEV: the TMPNN_PDL / TMPNN_TC_TRACE measurement switches)
 LIB_PATH = os.path.join(_HERE, "libthermompnn_b200_dev.so" if os.environ.get("TMPNN_LIB") == "dev" else "libthermompnn_b200.so")
 MAX_HIDDEN = 8
 

@@ -19,4 +19,4 @@ for name in CASES:
     e_ref = np.abs(ddg - ref)[ok].max(); e64 = np.abs(ddg - t64)[ok].max(); r64 = np.abs(ref - t64)[ok].max()
     worst = max(worst, e_ref)
     print(f"{name:18s} gpu-vs-ref {e_ref:.2e}   gpu-vs-fp64 {e64:.2e}   ref-vs-fp64 {r64:.2e}   rms gpu-vs-ref {np.sqrt(np.mean((ddg-ref)[ok]**2)):.2e}")
-print(f"worst gpu-vs-ref {worst:.2e}  (TMPNN_TC={os.environ.get('TMPNN_TC','7')})")
+print(f"worst gpu-vs-ref {worst:.2e}")
