@@ -232,13 +232,15 @@ struct Prep {
         std::memcpy(&r, &u, 4);
         return r;
     }
+    // (rows / columns outside the matrix are zero: narrow layers are padded to the 128 x 32 chunk shape)
     void put_tc(int64_t off, const std::string& name, int col0, int nchunks = 4, int row0 = 0) {
         int out, in;
         const float* W = find(name, &out, &in);
         for (int c = 0; c < nchunks; ++c)
             for (int n = 0; n < HID; ++n)
                 for (int kk = 0; kk < 32; ++kk) {
-                    const float x = W[(int64_t)(row0 + n) * in + col0 + c * 32 + kk];
+                    const int row = row0 + n, colk = col0 + c * 32 + kk;
+                    const float x = (row < out && colk < in) ? W[(int64_t)row * in + colk] : 0.f;
                     const float hi = rna_tf32(x), lo = rna_tf32(x - hi);
                     const int64_t idx = off + (int64_t)c * 8192 + n * 32 + ((((kk >> 2) ^ (n & 7)) << 2) | (kk & 3));
                     dev[idx] = hi;
@@ -341,6 +343,18 @@ DevLayout prepare_weights(Prep& P, const tmpnn_model_cfg& cfg) {
             for (int q = 0; q < 4; ++q) o += P.put_chunk(o, "both_out.1.weight", 0, (3 * q + s) * 32);
         for (int q = 0; q < 4; ++q) o += P.put_chunk(o, "both_out.3.weight", 0, 32 * q);
         for (int q = 0; q < 4; ++q) o += P.put_chunk(o, "both_out.5.weight", 0, 32 * q);
+        // the same as tensor-core images for the tcgen05 head (tc_head_kernels.cu), in its consumption order:
+        //   for j = 0..2: LA[j,0], LA[j,1], LA[j,2] (4 chunks each), both_out.1[:, j] (4) | both_out.3 (2) | both_out.5 (1)
+        L.tc_head = P.alloc((int64_t)51 * 8192);
+        {
+            int64_t t = L.tc_head;
+            for (int j = 0; j < 3; ++j) {
+                for (int k = 0; k < 3; ++k) { P.put_tc(t, "light_attention.feature_convolution.weight_center", HID * k, 4, HID * j); t += 4 * 8192; }
+                P.put_tc(t, "both_out.1.weight", HID * j); t += 4 * 8192;
+            }
+            P.put_tc(t, "both_out.3.weight", 0, 2); t += 2 * 8192;
+            P.put_tc(t, "both_out.5.weight", 0, 1);
+        }
         L.la_b = P.vec("light_attention.feature_convolution.bias");
         L.m1_b = P.vec("both_out.1.bias");
         L.m2_b = P.vec("both_out.3.bias");
@@ -566,8 +580,10 @@ int enqueue_pipeline(tmpnn_ctx* ctx, const RunIO& io, cudaStream_t st) {
                 h.weights = W; h.stream = L.head; h.Ws = L.Ws; h.la_b = L.la_b; h.m1_b = L.m1_b; h.m2_b = L.m2_b;
                 h.m3_b = L.m3_b; h.ddg = L.ddg;
                 h.dec_last = ctx->dec_last.p; h.dec_prev = ctx->dec_prev.p; h.S = d_S; h.table = io.table; h.N = N;
-                LaunchScope ls(ctx, st, "head");
-                launch_head(h, ctx->sm_count, st);
+                const bool tc = head_uses_tcgen05(N);
+                LaunchScope ls(ctx, st, tc ? "tc_head" : "head");
+                if (tc) launch_tc_head(h, L.tc_head, ctx->sm_count, st);
+                else launch_head(h, ctx->sm_count, st);
             } else {
                 HeadGenArgs h{};
                 h.weights = W; h.nlayers = L.gen_layers; h.relu_first = ctx->cfg.lightattn ? 0 : 1;
@@ -684,6 +700,7 @@ int tmpnn_create(int device, tmpnn_ctx** out) {
     if ((e = tc_kernels_init()) != cudaSuccess) return bail(std::string("tc_kernels_init: ") + cudaGetErrorString(e));
     if ((e = head_kernels_init()) != cudaSuccess) return bail(std::string("head_kernels_init: ") + cudaGetErrorString(e));
     if ((e = tc_node_kernels_init()) != cudaSuccess) return bail(std::string("tc_node_kernels_init: ") + cudaGetErrorString(e));
+    if ((e = tc_head_kernels_init()) != cudaSuccess) return bail(std::string("tc_head_kernels_init: ") + cudaGetErrorString(e));
 #ifdef TMPNN_DEV
     if (const char* env = std::getenv("TMPNN_TC_TRACE"))
         if (std::atoi(env)) { cudaMalloc(&ctx->d_trace, 3 * 512 * sizeof(long long)); cudaMemset(ctx->d_trace, 0, 3 * 512 * sizeof(long long)); }

@@ -92,5 +92,8 @@ void launch_tc_msg(bool dec, const float* hE, const int* E_idx, const float* P, 
 void launch_node_update(const NodeUpdArgs& a, int sms, cudaStream_t st);
 bool node_update_uses_tcgen05(int N);   // which form launch_node_update picks for a batch of N residues
 void launch_head(const HeadArgs& a, int sms, cudaStream_t st);
+bool head_uses_tcgen05(int N);           // large batches: tc_head_kernels.cu
+cudaError_t tc_head_kernels_init();
+void launch_tc_head(const HeadArgs& a, int64_t tc_img, int sms, cudaStream_t st);
 
 }  // namespace tmpnn

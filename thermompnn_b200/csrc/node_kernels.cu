@@ -325,6 +325,7 @@ cudaError_t node_kernels_init() {
 constexpr int NODE_MMA_MAX = 593;    // residues: up to here the clusters (one 16-residue tile each, 4 CTAs) fit in ONE wave on 148 SMs
 
 bool node_update_uses_tcgen05(int N) { return N >= NODE_MMA_MAX; }
+bool head_uses_tcgen05(int N) { return N >= NODE_MMA_MAX; }     // same boundary: above it the FP32 head is one long step-form wave
 
 void launch_node_update(const NodeUpdArgs& a, int sms, cudaStream_t st) {
     // Small batches: the warp-level tensor-core cluster form (node_mma_kernels.cu), one 16-residue tile per 4-CTA cluster,

@@ -5,12 +5,13 @@ import csv, io, json, os, re, subprocess, sys
 from collections import OrderedDict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02"       # raw files gpurun_out/<tag>_*
+otag = sys.argv[2] if len(sys.argv) > 2 else tag          # name of the committed summaries profiles/<otag>_*
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 
 KNAMES = {"tc_edge_kernel<0": "tc_edge_upd", "tc_edge_kernel<1": "tc_enc_msg", "tc_edge_kernel<2": "tc_dec_msg",
-          "tc_edge_feat_kernel": "tc_edge_feat", "node_update_step_kernel": "node_update", "node_update_kernel": "node_update",
-          "head_kernel": "head", "knn_kernel": "knn", "prep_nodes_kernel": "prep_nodes"}
+          "tc_edge_feat_kernel": "tc_edge_feat", "tc_node_update_kernel": "tc_node_update", "node_update_mma_kernel": "node_update",
+          "tc_head_kernel": "tc_head", "head_kernel": "head", "head_cluster_kernel": "head", "knn_kernel": "knn"}
 
 
 def short(name):
@@ -54,10 +55,11 @@ def launch_list(workload, cmd):
                 "| kernel | launches/step | us per launch | share |", "|---|---|---|---|"]
         for k, v in sorted(d["kernels"].items(), key=lambda kv: -kv[1]["share"]):
             out.append(f"| {k} | {v['launches_per_step']} | {v['us_per_launch']:.1f} | {100 * v['share']:.1f}% |")
-    open(os.path.join(P, f"{tag}_launches_{workload}.md"), "w").write("\n".join(out) + "\n")
+    open(os.path.join(P, f"{otag}_launches_{workload}.md"), "w").write("\n".join(out) + "\n")
 
 
 METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
+           "l1tex__m_xbar2l1tex_read_bytes.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor.sum",
            "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
            "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
@@ -73,12 +75,22 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
 
 def full_capture(workload, cmd, traffic):
     rep = os.path.join(G, f"{tag}_full_{workload}.ncu-rep")
-    if not os.path.exists(rep):
+    csvp = os.path.join(G, f"{tag}_full_{workload}.csv")        # already reduced on the GPU box (tools/round_artifacts.sh)
+    if os.path.exists(csvp):
+        txt = open(csvp).read()
+    elif os.path.exists(rep):
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    else:
         return
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     col = {h: i for i, h in enumerate(hdr)}
+    seen, uniq = set(), []                       # one capture per distinct kernel (the first)
+    for r in data:
+        k = r[col["Kernel Name"]]
+        if k not in seen:
+            seen.add(k); uniq.append(r)
+    data = uniq
     names = [short(r[col["Kernel Name"]]) for r in data]
     out = [f"# Round {tag[1:]}: `ncu --set full`, workload {workload.upper()}", "", f"Command: `{cmd}`", "",
            "| metric | unit | " + " | ".join(f"`{n[:34]}`" for n in names) + " |", "|---|---|" + "---|" * len(names)]
@@ -95,21 +107,23 @@ def full_capture(workload, cmd, traffic):
         if en and en not in traffic.setdefault(workload, {}):
             traffic[workload][en] = t
         out.append(f"- `{n[:60]}` ({en}): DRAM read+write per launch = {t / 1e6:.1f} MB")
-    open(os.path.join(P, f"{tag}_ncu_full_{workload}.md"), "w").write("\n".join(out) + "\n")
+    open(os.path.join(P, f"{otag}_ncu_full_{workload}.md"), "w").write("\n".join(out) + "\n")
 
 
 if __name__ == "__main__":
-    launch_list("c2", f"ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/{tag}_launches_c2.csv python bench.py --steps 2 --warmup 3 --no-cpu")
-    launch_list("c3", f"ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/{tag}_launches_c3.csv python bench.py --workload c3 --steps 2 --warmup 3 --no-cpu")
+    K = "tc_edge_kernel|tc_edge_feat|tc_node_update|node_update_mma|head_kernel|head_cluster|knn_kernel"
+    launch_list("c2", f"TMPNN_GRAPHS=0 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/{tag}_launches_c2.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-extra")
+    launch_list("c3", f"TMPNN_GRAPHS=0 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/{tag}_launches_c3.csv python bench.py --workload c3 --steps 2 --warmup 3 --no-cpu")
     traffic = {"note": "dram__bytes_read.sum + dram__bytes_write.sum per launch (bytes), first captured launch of each kernel, from the "
-                       f"ncu --set full captures summarised in profiles/{tag}_ncu_full_c2.md / _c3.md"}
-    full_capture("c3", f"ncu --set full --clock-control none --import-source on -k regex:'tc_edge_kernel|node_update' -s 45 -c 4 -o gpurun_out/{tag}_full_c3 python bench.py --workload c3 --steps 1 --warmup 3 --no-cpu", traffic)
-    full_capture("c2", f"ncu --set full --clock-control none --import-source on -k regex:'tc_edge_kernel|node_update' -s 45 -c 3 -o gpurun_out/{tag}_full_c2 python bench.py --steps 1 --warmup 3 --no-cpu", traffic)
-    json.dump(traffic, open(os.path.join(P, f"{tag}_traffic.json"), "w"), indent=1)
+                       f"ncu --set full captures summarised in profiles/{otag}_ncu_full_*.md"}
+    full_capture("c3", f"TMPNN_GRAPHS=0 ncu --set full --clock-control none --import-source on -k regex:'{K}' -s 36 -c 18 -o gpurun_out/{tag}_full_c3 python bench.py --workload c3 --steps 1 --warmup 3 --no-cpu", traffic)
+    full_capture("c2", f"TMPNN_GRAPHS=0 ncu --set full --clock-control none --import-source on -k regex:'{K}' -s 36 -c 18 -o gpurun_out/{tag}_full_c2 python bench.py --steps 1 --warmup 3 --no-cpu --no-extra", traffic)
+    full_capture("c5", f"TMPNN_GRAPHS=0 ncu --set full --clock-control none -k regex:'{K}' -s 18 -c 18 -o gpurun_out/{tag}_full_c5 python bench.py --workload c5 --steps 1 --warmup 3 --no-cpu", traffic)
+    json.dump(traffic, open(os.path.join(P, f"{otag}_traffic.json"), "w"), indent=1)
     lines = []
-    for w in ("c2", "c3", "c5", "ref", "c2_2gpu"):
+    for w in ("c2", "c3", "c4", "c5", "ref", "n2", "n8", "ref_n8"):
         bj = os.path.join(G, f"{tag}_bench_{w}.json")
         if os.path.exists(bj):
             lines.append(open(bj).read().strip())
-    open(os.path.join(P, f"{tag}_bench_lines.jsonl"), "w").write("\n".join(lines) + "\n")
-    print("wrote", sorted(f for f in os.listdir(P) if f.startswith(tag)))
+    open(os.path.join(P, f"{otag}_bench_lines.jsonl"), "w").write("\n".join(lines) + "\n")
+    print("wrote", sorted(f for f in os.listdir(P) if f.startswith(otag)))
