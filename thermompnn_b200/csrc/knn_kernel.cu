@@ -49,7 +49,7 @@ __global__ void knn_kernel(const int* __restrict__ offsets, int B, const float* 
     const int i = blockIdx.x * warps + w;
     if (i >= N) return;  // no block-level barriers below
     const int rowlen = NPL > 0 ? 0 : lmax;
-    float* d = s_row + (size_t)w * (2 * rowlen + 2 * KNB);    // row of keys | 48 selected values | 48 selected indices | candidate indices
+    float* d = s_row + (size_t)w * (rowlen + 2 * KNB);
     float* selv = d + rowlen;                             // [48] selected distances
     int* seli = reinterpret_cast<int*>(selv + KNB);       // [48] selected local indices
     // ---- this residue's protein: offsets[b] <= i < offsets[b+1]  (all lanes probe the sorted offsets at once)
@@ -171,57 +171,21 @@ __global__ void knn_kernel(const int* __restrict__ offsets, int B, const float* 
             d[j] = __fadd_rn(d[j], __fmul_rn(1.0f - m2, dmax));      // masked pairs pushed to the row maximum (:1105-1106)
         }
         __syncwarp();
-        // Pre-filter (long rows): the K-th smallest key of ANY subset of >= K elements is an upper bound U of the row's
-        // K-th smallest, so only keys <= U can be selected.  Subset = the 128 residues around i in the chain (spatially
-        // the closest ones): the 31 selection rounds then run over ~100-200 candidates instead of L keys.  Candidates are
-        // compacted in index order (keys in place over d[], indices in cidx[]), so ties still go to the lowest index.
-        int* cidx = reinterpret_cast<int*>(seli + KNB);   // [L]
-        int C = L;
-        {
-            const int il = i - s;
-            int w0 = il - 64; w0 = w0 < 0 ? 0 : (w0 + 128 > L ? L - 128 : w0);     // L > 512 here
-            uint32_t wk[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) wk[q] = __float_as_uint(d[w0 + lane + 32 * q]);
-            uint32_t U = 0;
-            for (int bit = 30; bit >= 0; --bit) {
-                const uint32_t trial = U | (1u << bit);
-                int cnt = (wk[0] < trial) + (wk[1] < trial) + (wk[2] < trial) + (wk[3] < trial);
-                cnt = __reduce_add_sync(0xffffffffu, cnt);
-                if (cnt < K) U = trial;
-            }
-            int n = 0;
-            for (int base = 0; base < L; base += 32) {
-                const int j = base + lane;
-                const uint32_t key = j < L ? __float_as_uint(d[j]) : 0xffffffffu;
-                const bool take = key <= U;
-                const uint32_t bt = __ballot_sync(0xffffffffu, take);
-                __syncwarp();                               // every lane has read its element of this chunk
-                if (take) {
-                    const int pos = n + __popc(bt & lt_mask);
-                    d[pos] = __uint_as_float(key);          // pos <= j: in-place compaction never overtakes the reads
-                    cidx[pos] = j;
-                }
-                n += __popc(bt);
-            }
-            C = n;
-            __syncwarp();
-        }
         uint32_t T = 0;
         for (int bit = 30; bit >= 0; --bit) {
             const uint32_t trial = T | (1u << bit);
             int cnt = 0;
-            for (int j = lane; j < C; j += 32) cnt += (__float_as_uint(d[j]) < trial) ? 1 : 0;
+            for (int j = lane; j < L; j += 32) cnt += (__float_as_uint(d[j]) < trial) ? 1 : 0;
             cnt = __reduce_add_sync(0xffffffffu, cnt);
             if (cnt < K) T = trial;
         }
         int n_less = 0;
-        for (int j = lane; j < C; j += 32) n_less += (__float_as_uint(d[j]) < T) ? 1 : 0;
+        for (int j = lane; j < L; j += 32) n_less += (__float_as_uint(d[j]) < T) ? 1 : 0;
         n_less = __reduce_add_sync(0xffffffffu, n_less);
         const int need_eq = K - n_less;                       // how many keys equal to T to take, in index order
-        for (int base = 0; base < C; base += 32) {
+        for (int base = 0; base < L; base += 32) {
             const int j = base + lane;
-            compact(j < C ? __float_as_uint(d[j]) : 0xffffffffu, j < C ? cidx[j] : 0, T, need_eq);
+            compact(j < L ? __float_as_uint(d[j]) : 0xffffffffu, j, T, need_eq);
         }
     }
     __syncwarp();
@@ -255,13 +219,13 @@ __global__ void knn_kernel(const int* __restrict__ offsets, int B, const float* 
 cudaError_t kernels_init() {
     return cudaFuncSetAttribute(knn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
-int knn_max_len() { return (200 * 1024 / 4 - 2 * KNB) / 2; }
+int knn_max_len() { return 200 * 1024 / 4 - 2 * KNB; }
 
 void launch_knn(const int* offsets, int B, const float* X, const uint8_t* mask, const int* S_in, int N, int lmax, float* atoms,
                 float* maskf, int* S_out, int* err_flag, int* E_idx, float* D_nb, float* cnt_enc, float* cnt_dec, cudaStream_t st) {
     int warps = 8;
     const int rowlen = lmax <= 512 ? 0 : lmax;            // register-resident rows up to 512 residues
-    const size_t per_warp = (size_t)(2 * rowlen + 2 * KNB) * 4;
+    const size_t per_warp = (size_t)(rowlen + 2 * KNB) * 4;
     while (warps > 1 && (size_t)warps * per_warp > 200 * 1024) warps >>= 1;
     const size_t smem = (size_t)warps * per_warp;
     const dim3 grid((N + warps - 1) / warps), block(warps * 32);

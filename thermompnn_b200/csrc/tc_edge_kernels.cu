@@ -32,22 +32,19 @@ constexpr uint32_t TC_WCHUNK_BYTES = 32768;   // [128 n][32 k] hi (16 KB) | lo (
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ uint32_t rna_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
-// x = hi + lo (+ <= 2^-22 |x|), both representable in tf32
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-    hi = rna_tf32(x);
-    lo = rna_tf32(x - __uint_as_float(hi));
-}
-
-// Write 32 values as columns [32c, 32c+32) of the next A operand (hi and lo planes) and publish the chunk.
+// Write 32 values as columns [32c, 32c+32) of the next A operand and publish the chunk.  hi plane: the tf32 the tensor
+// core would read anyway (truncation); lo plane: the exact remainder (packed: fma(hi, -1, v)), as in publish_A16.
 __device__ __forceinline__ void publish_A_chunk(uint32_t lane_addr, int c, const float (&v)[32], uint64_t* a_ready) {
     uint32_t hi[32], lo[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) split_tf32(v[j], hi[j], lo[j]);
+    for (int j = 0; j < 32; j += 2) {
+        hi[j] = __float_as_uint(v[j]) & 0xffffe000u;
+        hi[j + 1] = __float_as_uint(v[j + 1]) & 0xffffe000u;
+        float l0, l1;
+        upk2(fma2(pk2(__uint_as_float(hi[j]), __uint_as_float(hi[j + 1])), pk2(-1.0f, -1.0f), pk2(v[j], v[j + 1])), l0, l1);
+        lo[j] = __float_as_uint(l0);
+        lo[j + 1] = __float_as_uint(l1);
+    }
     tmem_st32(lane_addr + COL_AHI + c * 32, hi);
     tmem_st32(lane_addr + COL_ALO + c * 32, lo);
     tmem_wait_st();
@@ -572,6 +569,7 @@ __global__ void __launch_bounds__((4 * NSETS + 2 + NAP) * 32, 1) tc_edge_kernel(
 // into the A operand) -> edge_embedding (416 -> 128, 13 K-chunks through 4 recycled A slots) -> LayerNorm
 // (thread-local) -> W_e + b  => h_E          (protein_mpnn_utils.py:1111-1125, 1142-1179, 1229)
 // ---------------------------------------------------------------------------------------------------------
+constexpr float RBF_C = 0.8f * 1.2011224087864498f;    // (1 / sigma) * sqrt(log2 e), sigma = 1.25 (protein_mpnn_utils.py:1115-1118)
 __constant__ int8_t c_tc_pair_a[NPAIR] = {1, 0, 2, 3, 4, 1, 1, 1, 1, 0, 0, 0, 4, 4, 3, 0, 2, 3, 4, 2, 3, 4, 2, 3, 2};
 __constant__ int8_t c_tc_pair_b[NPAIR] = {1, 0, 2, 3, 4, 0, 2, 3, 4, 2, 3, 4, 2, 3, 2, 1, 1, 1, 1, 0, 0, 0, 4, 4, 3};
 
@@ -584,7 +582,7 @@ struct __align__(1024) TcFeatSmem {
     int posq[TC_ROWS];
     float pos_table[66 * 16];
     float vec[3][HID];                           // LN gain, LN shift, W_e bias
-    float mu[16];
+    float muc[16];                               // -c mu_t, c = 0.8 sqrt(log2 e)  (RBF centres pre-scaled for the ex2 form)
     float2 lnx[2][TC_ROWS];
     uint64_t w_full[TC_WSLOTS], w_empty[TC_WSLOTS];
     uint64_t a_ready[4], a_free[4];
@@ -629,7 +627,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tc_edge_feat_kernel(TcFeatArgs 
     }
     for (int i = threadIdx.x; i < HID; i += T2_THREADS) { S.vec[0][i] = a.ln_g[i]; S.vec[1][i] = a.ln_b[i]; S.vec[2][i] = a.b_e[i]; }
     for (int i = threadIdx.x; i < 66 * 16; i += T2_THREADS) S.pos_table[i] = a.pos_table[i];
-    if (threadIdx.x < 16) S.mu[threadIdx.x] = a.rbf_mu[threadIdx.x];
+    if (threadIdx.x < 16) S.muc[threadIdx.x] = -RBF_C * a.rbf_mu[threadIdx.x];
     if (warp == 8) tmem_alloc<512>(&S.tmem_base);
     tc_fence_before();
     __syncthreads();
@@ -766,10 +764,18 @@ __global__ void __launch_bounds__(T2_THREADS, 1) tc_edge_feat_kernel(TcFeatArgs 
                             const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
                             D = __fsqrt_rn(__fadd_rn(d2, 1e-6f));
                         }
+                        // rbf_t = exp(-((D - mu_t) / 1.25)^2) = 2^(-(c D - c mu_t)^2), c = 0.8 sqrt(log2 e); two per instruction
+                        const float cD = D * RBF_C;
+                        const f32x2 cd2 = pk2(cD, cD);
 #pragma unroll
-                        for (int t = 0; t < 16; ++t) {
-                            const float z = (D - S.mu[t]) * 0.8f;          // / sigma, sigma = 1.25
-                            v[h * 16 + t] = __expf(-(z * z));
+                        for (int t = 0; t < 16; t += 2) {
+                            const f32x2 u = add2(cd2, pk2(S.muc[t], S.muc[t + 1]));     // muc = -c mu
+                            float w0, w1, e0, e1;
+                            upk2(mul2(u, u), w0, w1);
+                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(-w0));
+                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(-w1));
+                            v[h * 16 + t] = e0;
+                            v[h * 16 + t + 1] = e1;
                         }
                     }
                 }

@@ -97,6 +97,7 @@ class ShardedScan:
         self.flat = torch.zeros((self.world, self.plan.max_rows, 21), dtype=torch.float32, device=self.device)
         self.host = torch.empty((self.world, self.plan.max_rows, 21), dtype=torch.float32).pin_memory()
         self._dev_in = None
+        self._stream = torch.cuda.Stream(device=self.device)   # run(): kernels, collective and the D2H are ordered on this stream
 
     # -- inputs ---------------------------------------------------------------------------------------------------
     def host_inputs(self):
@@ -129,9 +130,10 @@ class ShardedScan:
 
     def run(self, inputs=None) -> List[np.ndarray]:
         """All tables, in input order, on the host (every rank gets all of them)."""
-        st = torch.cuda.current_stream(self.device)
-        self.compute_local(inputs, stream=st.cuda_stream)
-        self.gather()
-        self.host.copy_(self.flat, non_blocking=True)
+        st = self._stream
+        with torch.cuda.stream(st):
+            self.compute_local(inputs, stream=st.cuda_stream)
+            self.gather()
+            self.host.copy_(self.flat, non_blocking=True)
         st.synchronize()
         return [t.copy() for t in self.plan.unpack(self.host.numpy())]
