@@ -121,7 +121,7 @@ if __name__ == "__main__":
     full_capture("c5", f"TMPNN_GRAPHS=0 ncu --set full --clock-control none -k regex:'{K}' -s 18 -c 18 -o gpurun_out/{tag}_full_c5 python bench.py --workload c5 --steps 1 --warmup 3 --no-cpu", traffic)
     json.dump(traffic, open(os.path.join(P, f"{otag}_traffic.json"), "w"), indent=1)
     lines = []
-    for w in ("c2", "c3", "c4", "c5", "ref", "n2", "n8", "ref_n8"):
+    for w in ("c2", "c3", "c4", "c5", "ref", "n2", "n4", "n8", "c5_n1"):
         bj = os.path.join(G, f"{tag}_bench_{w}.json")
         if os.path.exists(bj):
             lines.append(open(bj).read().strip())
