@@ -222,6 +222,11 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NC_THREADS, 1) head_
     pdl_trigger();
 #pragma unroll
     for (int k = 0; k < NC_SLOTS; ++k) { issue(k, k); cp_async_commit(); }
+    // this thread's bias values: constants, fetched before the dependency wait (after a cluster.sync, which invalidates
+    // L1, each would be an exposed L2 round trip inside the six-phase chain)
+    const float c_la0 = __ldg(wb + a.la_b + n), c_la1 = __ldg(wb + a.la_b + HID + n), c_la2 = __ldg(wb + a.la_b + 2 * HID + n);
+    const float c_m1 = n < 64 ? __ldg(wb + a.m1_b + n) : 0.f, c_m2 = n < 32 ? __ldg(wb + a.m2_b + n) : 0.f;
+    const float c_m3 = n < 21 ? __ldg(wb + a.m3_b + n) : 0.f, c_sc = __ldg(wb + a.ddg), c_sh = __ldg(wb + a.ddg + 1);
     pdl_wait();
     for (int i = threadIdx.x; i < NT * HID; i += NC_THREADS) {
         int t = i / HID, c = i % HID, node = node0 + t;
@@ -258,7 +263,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NC_THREADS, 1) head_
     phase(res, 3, 0, x, 3 * HID);
     issue(9, 0); issue(10, 1); issue(11, 2); cp_async_commit();      // slots 0..2 are free (cluster barrier above)
     {
-        const float b = __ldg(wb + a.la_b + n);
+        const float b = c_la0;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) y[(g + 4 * j) * 3 * HID + n] = fmaxf(res[j] + b, 0.f);
     }
@@ -266,14 +271,14 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NC_THREADS, 1) head_
     phase(res, 3, 3, x, 3 * HID);
     issue(12, 3); issue(13, 4); cp_async_commit();
     {
-        const float b = __ldg(wb + a.la_b + HID + n);
+        const float b = c_la1;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) y[(g + 4 * j) * 3 * HID + HID + n] = fmaxf(res[j] + b, 0.f);
     }
     cp_async_wait<2>(); __syncthreads();             // chunks 6..8
     phase(res, 3, 6, x, 3 * HID);
     {
-        const float b = __ldg(wb + a.la_b + 2 * HID + n);
+        const float b = c_la2;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) y[(g + 4 * j) * 3 * HID + 2 * HID + n] = fmaxf(res[j] + b, 0.f);
     }
@@ -281,21 +286,21 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NC_THREADS, 1) head_
     cp_async_wait<1>(); __syncthreads();             // chunks 9..11 + y
     phase(res, 3, 0, y, 3 * HID);
     {
-        const float b = n < 64 ? __ldg(wb + a.m1_b + n) : 0.f;
+        const float b = c_m1;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) x[(g + 4 * j) * HID + n] = fmaxf(res[j] + b, 0.f);   // z1 (columns >= 64 are 0)
     }
     cp_async_wait<0>(); __syncthreads();             // chunks 12, 13 + z1
     phase(res, 1, 3, x, HID);
     {
-        const float b = n < 32 ? __ldg(wb + a.m2_b + n) : 0.f;
+        const float b = c_m2;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) y[(g + 4 * j) * HID + n] = fmaxf(res[j] + b, 0.f);   // z2 (columns >= 32 are 0)
     }
     __syncthreads();
     phase(res, 1, 4, y, HID);
     if (q == 0 && n < 21) {
-        const float b = __ldg(wb + a.m3_b + n), sc = __ldg(wb + a.ddg), sh = __ldg(wb + a.ddg + 1);
+        const float b = c_m3, sc = c_sc, sh = c_sh;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
             int node = node0 + g + 4 * j;

@@ -81,8 +81,8 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NM_THREADS, 1) node_
     float* hid = x + NM_T * NM_P;                    // [16][NM_P]  this CTA's block of the FFN hidden layer
     float* xr0 = hid + NM_T * NM_P;                  // [16][128]   this CTA's partials, read by the other three CTAs
     float* xr1 = xr0 + NM_T * HID;                   //             (one buffer per all-reduce: no second cluster barrier)
-    float* red = xr1 + NM_T * HID;                   // [16 warps][16 rows]
-    float* cnt_s = red + 16 * NM_T;                  // [16]
+    float2* red = reinterpret_cast<float2*>(xr1 + NM_T * HID);   // [2 LayerNorms][16 warps][16 rows] (mean, M2) partials
+    float* cnt_s = reinterpret_cast<float*>(red + 2 * 16 * NM_T);   // [16]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     const int ncol = 8 * warp + g;                   // B-fragment column of this lane
@@ -107,6 +107,12 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NM_THREADS, 1) node_
     pdl_trigger();
 #pragma unroll
     for (int k = 0; k < NM_SLOTS; ++k) issue(k, k);
+    // This lane's slices of the bias / LayerNorm vectors: constants, fetched before the dependency wait (each would
+    // otherwise be an exposed L2 round trip in the middle of the chain -- cluster.sync invalidates L1)
+    auto ld2 = [&](int64_t off) { return __ldg(reinterpret_cast<const float2*>(wb + off + c0)); };
+    const float2 c_b3 = ld2(a.w.b3), c_n1g = ld2(a.w.n1.g), c_n1b = ld2(a.w.n1.b), c_bin = ld2(a.w.bin + q * HID), c_bout = ld2(a.w.bout),
+                 c_n2g = ld2(a.w.n2.g), c_n2b = ld2(a.w.n2.b);
+    const float2 c_pb = (has_proj && a.proj[q].bias >= 0) ? ld2(a.proj[q].bias) : make_float2(0.f, 0.f);
     NM_STAMP(1);
     pdl_wait();                                      // everything below reads earlier kernels' output
     NM_STAMP(2);
@@ -125,8 +131,13 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NM_THREADS, 1) node_
     }
     if (threadIdx.x < NM_T) cnt_s[threadIdx.x] = (node0 + threadIdx.x < a.N) ? a.cnt_pre[node0 + threadIdx.x] : 0.f;
     float hv[4];                                     // h_V at (g, c0), (g, c0+1), (g+8, c0), (g+8, c0+1)
+    float2 tv0 = make_float2(0.f, 0.f), tv1 = tv0;   // rows of the per-letter table this CTA's projection adds (decoder Q)
     {
         const int n0 = node0 + g, n1 = node0 + g + 8;
+        if (has_proj && a.proj[q].table >= 0) {      // requested now, used at the very end
+            if (n0 < a.N) tv0 = __ldg(reinterpret_cast<const float2*>(wb + a.proj[q].table + (size_t)a.S[n0] * HID + c0));
+            if (n1 < a.N) tv1 = __ldg(reinterpret_cast<const float2*>(wb + a.proj[q].table + (size_t)a.S[n1] * HID + c0));
+        }
         const float2 v0 = n0 < a.N ? *reinterpret_cast<const float2*>(a.hV + (size_t)n0 * HID + c0) : make_float2(0.f, 0.f);
         const float2 v1 = n1 < a.N ? *reinterpret_cast<const float2*>(a.hV + (size_t)n1 * HID + c0) : make_float2(0.f, 0.f);
         hv[0] = v0.x; hv[1] = v0.y; hv[2] = v1.x; hv[3] = v1.y;
@@ -135,7 +146,9 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NM_THREADS, 1) node_
     auto cluster_allreduce = [&](float (&v)[4], float* xr) {
         *reinterpret_cast<float2*>(xr + g * HID + c0) = make_float2(v[0], v[1]);
         *reinterpret_cast<float2*>(xr + (g + 8) * HID + c0) = make_float2(v[2], v[3]);
+        if (xr == xr0) NM_STAMP(13);
         cluster.sync();
+        if (xr == xr0) NM_STAMP(14);
         float2 p[4][2];
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
@@ -148,32 +161,34 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NM_THREADS, 1) node_
         v[2] = (p[0][1].x + p[1][1].x) + (p[2][1].x + p[3][1].x);
         v[3] = (p[0][1].y + p[1][1].y) + (p[2][1].y + p[3][1].y);
     };
-    // LayerNorm over the 128 columns of rows g and g + 8 (two-pass); block-wide barriers inside
-    auto layernorm = [&](float (&v)[4], const float* __restrict__ gam, const float* __restrict__ bet) {
+    // LayerNorm over the 128 columns of rows g and g + 8: every warp reduces its 8 columns to (mean, M2) per row, the 16
+    // partials are combined in warp order (Chan et al.: equal counts) -- ONE block barrier; `red` is a fresh buffer per call
+    auto layernorm = [&](float (&v)[4], const float2 gg, const float2 bb, float2* red) {
         float s0 = v[0] + v[1], s1 = v[2] + v[3];
         s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
         s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-        if (t == 0) { red[warp * NM_T + g] = s0; red[warp * NM_T + g + 8] = s1; }
+        const float mw0 = s0 * 0.125f, mw1 = s1 * 0.125f;
+        float e0 = v[0] - mw0, e1 = v[1] - mw0, e2 = v[2] - mw1, e3 = v[3] - mw1;
+        float q0 = fmaf(e0, e0, e1 * e1), q1 = fmaf(e2, e2, e3 * e3);
+        q0 += __shfl_xor_sync(0xffffffffu, q0, 1); q0 += __shfl_xor_sync(0xffffffffu, q0, 2);
+        q1 += __shfl_xor_sync(0xffffffffu, q1, 1); q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
+        if (t == 0) { red[warp * NM_T + g] = make_float2(mw0, q0); red[warp * NM_T + g + 8] = make_float2(mw1, q1); }
         __syncthreads();
         float m0 = 0.f, m1 = 0.f;
 #pragma unroll
-        for (int w = 0; w < 16; ++w) { m0 += red[w * NM_T + g]; m1 += red[w * NM_T + g + 8]; }
-        m0 *= (1.0f / HID); m1 *= (1.0f / HID);
-        __syncthreads();
-        const float d0 = v[0] - m0, d1 = v[1] - m0, d2 = v[2] - m1, d3 = v[3] - m1;
-        float q0 = fmaf(d0, d0, d1 * d1), q1 = fmaf(d2, d2, d3 * d3);
-        q0 += __shfl_xor_sync(0xffffffffu, q0, 1); q0 += __shfl_xor_sync(0xffffffffu, q0, 2);
-        q1 += __shfl_xor_sync(0xffffffffu, q1, 1); q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
-        if (t == 0) { red[warp * NM_T + g] = q0; red[warp * NM_T + g + 8] = q1; }
-        __syncthreads();
+        for (int w = 0; w < 16; ++w) { m0 += red[w * NM_T + g].x; m1 += red[w * NM_T + g + 8].x; }
+        m0 *= (1.0f / 16.0f); m1 *= (1.0f / 16.0f);
         float v0 = 0.f, v1 = 0.f;
 #pragma unroll
-        for (int w = 0; w < 16; ++w) { v0 += red[w * NM_T + g]; v1 += red[w * NM_T + g + 8]; }
+        for (int w = 0; w < 16; ++w) {
+            const float2 a0 = red[w * NM_T + g], a1 = red[w * NM_T + g + 8];
+            const float d0 = a0.x - m0, d1 = a1.x - m1;
+            v0 += fmaf(8.0f * d0, d0, a0.y);
+            v1 += fmaf(8.0f * d1, d1, a1.y);
+        }
         const float r0 = 1.0f / sqrtf(v0 * (1.0f / HID) + LN_EPS), r1 = 1.0f / sqrtf(v1 * (1.0f / HID) + LN_EPS);
-        const float2 gg = __ldg(reinterpret_cast<const float2*>(gam + c0)), bb = __ldg(reinterpret_cast<const float2*>(bet + c0));
-        v[0] = d0 * r0 * gg.x + bb.x; v[1] = d1 * r0 * gg.y + bb.y;
-        v[2] = d2 * r1 * gg.x + bb.x; v[3] = d3 * r1 * gg.y + bb.y;
-        __syncthreads();                             // red may be reused
+        v[0] = (v[0] - m0) * r0 * gg.x + bb.x; v[1] = (v[1] - m0) * r0 * gg.y + bb.y;
+        v[2] = (v[2] - m1) * r1 * gg.x + bb.x; v[3] = (v[3] - m1) * r1 * gg.y + bb.y;
     };
     auto store_tile = [&](float* dst, const float (&v)[4]) {
         *reinterpret_cast<float2*>(dst + g * NM_P + c0) = make_float2(v[0], v[1]);
@@ -194,12 +209,12 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NM_THREADS, 1) node_
     cluster_allreduce(am, xr0);
     NM_STAMP(5);
     {
-        const float2 b3 = __ldg(reinterpret_cast<const float2*>(wb + a.w.b3 + c0));
+        const float2 b3 = c_b3;
         const float cg0 = cnt_s[g], cg1 = cnt_s[g + 8];
         h[0] = hv[0] + fmaf(cg0, b3.x, am[0]) / MSG_SCALE; h[1] = hv[1] + fmaf(cg0, b3.y, am[1]) / MSG_SCALE;
         h[2] = hv[2] + fmaf(cg1, b3.x, am[2]) / MSG_SCALE; h[3] = hv[3] + fmaf(cg1, b3.y, am[3]) / MSG_SCALE;
     }
-    layernorm(h, wb + a.w.n1.g, wb + a.w.n1.b);      // ends with a barrier: x is free
+    layernorm(h, c_n1g, c_n1b, red); // (x is free: every warp passed the barrier inside after its W3 reads)
     NM_STAMP(6);
     store_tile(x, h);
     // ---- FFN 128 -> 512: this CTA's hidden block q
@@ -210,7 +225,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NM_THREADS, 1) node_
 #pragma unroll
     for (int s = 0; s < 4; ++s) mma_chunk(am, ac, x + 32 * s, ring + (1 + s) * WCHUNK_FLOATS, g, t, ncol);
     {
-        const float2 bi = __ldg(reinterpret_cast<const float2*>(wb + a.w.bin + q * HID + c0));
+        const float2 bi = c_bin;
         float v[4] = {gelu_erf(am[0] + ac[0] + bi.x), gelu_erf(am[1] + ac[1] + bi.y), gelu_erf(am[2] + ac[2] + bi.x),
                       gelu_erf(am[3] + ac[3] + bi.y)};
         store_tile(hid, v);
@@ -232,10 +247,10 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NM_THREADS, 1) node_
     cluster_allreduce(am, xr1);
     NM_STAMP(9);
     {
-        const float2 bo = __ldg(reinterpret_cast<const float2*>(wb + a.w.bout + c0));
+        const float2 bo = c_bout;
         h[0] += am[0] + bo.x; h[1] += am[1] + bo.y; h[2] += am[2] + bo.x; h[3] += am[3] + bo.y;
     }
-    layernorm(h, wb + a.w.n2.g, wb + a.w.n2.b);
+    layernorm(h, c_n2g, c_n2b, red + 16 * NM_T);
     NM_STAMP(10);
     {
         const int n0 = node0 + g, n1 = node0 + g + 8;
@@ -262,16 +277,14 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NM_THREADS, 1) node_
 #pragma unroll
         for (int s = 0; s < 4; ++s) mma_chunk(am, ac, x + 32 * s, ring + (1 + s) * WCHUNK_FLOATS, g, t, ncol);
         const ProjSpec ps = a.proj[q];
-        const float2 b = ps.bias >= 0 ? __ldg(reinterpret_cast<const float2*>(wb + ps.bias + c0)) : make_float2(0.f, 0.f);
+        const float2 b = c_pb;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             const int node = node0 + g + 8 * half;
             if (node < a.N) {
                 float2 v = make_float2(am[2 * half] + ac[2 * half] + b.x, am[2 * half + 1] + ac[2 * half + 1] + b.y);
-                if (ps.table >= 0) {
-                    const float2 tv = __ldg(reinterpret_cast<const float2*>(wb + ps.table + (size_t)a.S[node] * HID + c0));
-                    v.x += tv.x; v.y += tv.y;
-                }
+                const float2 tv = half ? tv1 : tv0;
+                v.x += tv.x; v.y += tv.y;
                 *reinterpret_cast<float2*>(ps.out + (size_t)node * HID + c0) = v;
             }
         }
@@ -283,7 +296,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NM_THREADS, 1) node_
 }
 
 static size_t smem_node_mma() {
-    return sizeof(float) * (NM_SLOTS * WCHUNK_FLOATS + 2 * NM_T * NM_P + 2 * NM_T * HID + 16 * NM_T + NM_T);
+    return sizeof(float) * (NM_SLOTS * WCHUNK_FLOATS + 2 * NM_T * NM_P + 2 * NM_T * HID + 2 * 2 * 16 * NM_T + NM_T);
 }
 
 cudaError_t node_mma_kernels_init() {

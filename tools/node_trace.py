@@ -14,4 +14,4 @@ names = ["start", "ring issued", "pdl_wait done", "inputs loaded", "W3 fma done"
 for it in range(3):
     eng.run(p.offsets, p.X, p.S, p.residue_idx, p.chain_enc, p.mask)
     t = eng.fetch_node_trace()
-    print("run", it, " ".join(f"{n}={int(t[i] - t[0])}" for i, n in enumerate(names)))
+    print("run", it, " ".join(f"{n}={int(t[i] - t[0])}" for i, n in enumerate(names)), f"| AR1: before cluster.sync={int(t[13] - t[0])} after={int(t[14] - t[0])}")
