@@ -421,3 +421,27 @@ def test_tied_masked_neighbours_are_implementation_defined(gpu_model, oracle_wei
     _, ref, _ = O.ssm_table(oracle_weights, pdb)
     print("tie-order sensitivity of the reference model itself: max |ddG_gpu - ddG_cpu_topk| =",
           float(np.abs(ddg - ref.numpy())[valid].max()))
+
+
+def test_edge_states_match_oracle_on_every_edge(gpu_model, oracle_weights):
+    """The reference fixtures keep h_E for six residues per case (size); the oracle, pinned to those, gives every edge:
+    h_E after W_e and after each encoder layer, all residues, all 48 slots (matched by neighbour index)."""
+    from oracle import thermompnn_oracle as O
+    eng = gpu_model._get_engine()
+    for pdb in (synth(64, 21), synth(77, 9, gaps=[10, 11, 40]), synth_multichain([40, 45], 14)):
+        tr = {}
+        O.ssm_table(oracle_weights, pdb, trace=tr)
+        p = featurize_batch([pdb])
+        L, valid = p.n_residues, p.mask.astype(bool)
+        ref_idx = tr["E_idx"].numpy()
+        try:
+            for stage, key in ((2, "h_E0"), (3, "enc0_h_E"), (4, "enc1_h_E"), (5, "enc2_h_E")):
+                eng.set_debug_stop(stage)
+                eng.run(p.offsets, p.X, p.S, p.residue_idx, p.chain_enc, p.mask)
+                E_idx, hE = eng.fetch("E_idx"), eng.fetch("h_E")
+                same = (E_idx == ref_idx) & valid[:, None]           # gap rows pick arbitrary (all-tie) neighbours
+                assert same[valid].mean() > 0.98
+                err = np.abs(hE - tr[key].numpy())[same].max()
+                assert err <= 2e-4, (pdb["name"], key, err)
+        finally:
+            eng.set_debug_stop(0)

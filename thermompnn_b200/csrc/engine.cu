@@ -332,17 +332,28 @@ DevLayout prepare_weights(Prep& P, const tmpnn_model_cfg& cfg) {
     L.Wout = P.vec(pm + "W_out.weight");
     L.bout = P.vec(pm + "W_out.bias");
     if (cfg.has_head && cfg_is_default(cfg)) {
-        // head weights in step order (14 steps, all K-split: group q = rows (q*steps + s)*32.. of the phase's matrix)
-        L.head = P.alloc((int64_t)56 * 4096);
-        int64_t o = L.head;
-        for (int blk = 0; blk < 3; ++blk)
-            for (int s = 0; s < 3; ++s)
-                for (int q = 0; q < 4; ++q)
-                    o += P.put_chunk(o, "light_attention.feature_convolution.weight_center", blk * HID, (3 * q + s) * 32);
-        for (int s = 0; s < 3; ++s)
-            for (int q = 0; q < 4; ++q) o += P.put_chunk(o, "both_out.1.weight", 0, (3 * q + s) * 32);
-        for (int q = 0; q < 4; ++q) o += P.put_chunk(o, "both_out.3.weight", 0, 32 * q);
-        for (int q = 0; q < 4; ++q) o += P.put_chunk(o, "both_out.5.weight", 0, 32 * q);
+        // Small-batch head (node_mma_kernels.cu: head_mma_kernel): per CTA q of the 4-CTA cluster one contiguous block
+        //   LA[:, 96q..96q+96) as [384 k][96 n] | both_out.1[:, 96q..) as [96 k][64 n] | both_out.3 [64 k][32 n] | both_out.5 [32 k][32 n]
+        // stored as the kernel keeps it in shared memory: element (k, n) at k * NC + (n ^ ((k & 3) << 3)).
+        L.head_mma = P.alloc((int64_t)4 * 46080);
+        {
+            auto put = [&](int64_t off, const std::string& name, int K, int NC, int out0, int in0) {
+                int out, in;
+                const float* W = P.find(name, &out, &in);
+                for (int k = 0; k < K; ++k)
+                    for (int n = 0; n < NC; ++n) {
+                        const int o = out0 + n, i = in0 + k;
+                        P.dev[off + (int64_t)k * NC + (n ^ ((k & 3) << 3))] = (o < out && i < in) ? W[(int64_t)o * in + i] : 0.f;
+                    }
+            };
+            for (int q = 0; q < 4; ++q) {
+                int64_t o = L.head_mma + (int64_t)q * 46080;
+                put(o, "light_attention.feature_convolution.weight_center", 384, 96, 96 * q, 0); o += 384 * 96;
+                put(o, "both_out.1.weight", 96, 64, 0, 96 * q); o += 96 * 64;
+                put(o, "both_out.3.weight", 64, 32, 0, 0); o += 64 * 32;
+                put(o, "both_out.5.weight", 32, 32, 0, 0);
+            }
+        }
         // the same as tensor-core images for the tcgen05 head (tc_head_kernels.cu), in its consumption order:
         //   for j = 0..2: LA[j,0], LA[j,1], LA[j,2] (4 chunks each), both_out.1[:, j] (4) | both_out.3 (2) | both_out.5 (1)
         L.tc_head = P.alloc((int64_t)51 * 8192);
@@ -577,13 +588,13 @@ int enqueue_pipeline(tmpnn_ctx* ctx, const RunIO& io, cudaStream_t st) {
         if (io.table) {
             if (cfg_is_default(ctx->cfg)) {
                 HeadArgs h{};
-                h.weights = W; h.stream = L.head; h.Ws = L.Ws; h.la_b = L.la_b; h.m1_b = L.m1_b; h.m2_b = L.m2_b;
+                h.weights = W; h.Ws = L.Ws; h.la_b = L.la_b; h.m1_b = L.m1_b; h.m2_b = L.m2_b;
                 h.m3_b = L.m3_b; h.ddg = L.ddg;
                 h.dec_last = ctx->dec_last.p; h.dec_prev = ctx->dec_prev.p; h.S = d_S; h.table = io.table; h.N = N;
                 const bool tc = head_uses_tcgen05(N);
                 LaunchScope ls(ctx, st, tc ? "tc_head" : "head");
                 if (tc) launch_tc_head(h, L.tc_head, ctx->sm_count, st);
-                else launch_head(h, ctx->sm_count, st);
+                else launch_head_mma(h, L.head_mma, st);
             } else {
                 HeadGenArgs h{};
                 h.weights = W; h.nlayers = L.gen_layers; h.relu_first = ctx->cfg.lightattn ? 0 : 1;

@@ -31,7 +31,7 @@ struct NodeUpdArgs {
 
 struct HeadArgs {
     const float* weights;
-    int64_t stream, Ws, la_b, m1_b, m2_b, m3_b, ddg;
+    int64_t Ws, la_b, m1_b, m2_b, m3_b, ddg;
     const float* dec_last;  // [N][128] output of the last decoder layer
     const float* dec_prev;  // [N][128] output of the one before
     const int* S;
@@ -91,7 +91,7 @@ void launch_tc_msg(bool dec, const float* hE, const int* E_idx, const float* P, 
                    long long* trace = nullptr);
 void launch_node_update(const NodeUpdArgs& a, int sms, cudaStream_t st);
 bool node_update_uses_tcgen05(int N);   // which form launch_node_update picks for a batch of N residues
-void launch_head(const HeadArgs& a, int sms, cudaStream_t st);
+void launch_head_mma(const HeadArgs& a, int64_t wstream, cudaStream_t st);   // small batches: node_mma_kernels.cu
 bool head_uses_tcgen05(int N);           // large batches: tc_head_kernels.cu
 cudaError_t tc_head_kernels_init();
 void launch_tc_head(const HeadArgs& a, int64_t tc_img, int sms, cudaStream_t st);

@@ -295,12 +295,165 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NM_THREADS, 1) node_
     NM_STAMP(12);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// head, small batches:  x = [dec3 | dec2 | W_s[S]] (384) -> y = LA centre tap . x + b -> (ReLU, Linear) x3 -> affine  => T[N][21]
+// (transfer_model.py:82-83, 96-116, 140-155).  The same 4-CTA cluster per 16-residue tile, ONE all-reduce:
+//   LA     N-split   CTA q: output columns [96q, 96q+96) over the full K = 384 (every CTA holds the whole x tile)
+//   MLP1   K-split   CTA q: exactly those 96 columns of relu(y) are its K slice -> partial [16][64] -> cluster all-reduce
+//   MLP2, MLP3       tiny (64 -> 32 -> 21): computed by every CTA from the reduced z1, no exchange; CTA 0 stores
+// (The FP32 form this replaces K-split every phase: six all-reduces, 25 us for one 300-residue protein.)
+// The CTA's weights (184 KB: LA slice [384 k][96 n] | W1 slice [96][64] | W2 [64][32] | W3 [32][32]) are requested in one
+// go before the dependency wait; engine.cu stores them pre-swizzled (16-byte granules XOR (k & 3), see mma_chunk).
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+constexpr int HM_XP = 3 * HID + 4;    // x tile row pitch (388: conflict-free A-fragment loads)
+constexpr int HM_YP = 96 + 4, HM_Z1P = 64 + 4, HM_Z2P = 32 + 4;
+constexpr int HM_WLA = 384 * 96, HM_W1 = 96 * 64, HM_W2 = 64 * 32, HM_W3 = 32 * 32;
+constexpr int HM_WFLOATS = HM_WLA + HM_W1 + HM_W2 + HM_W3;     // 46080 floats per CTA
+
+// acc += A[16][8 nk] . W[8 nk][NC] restricted to this warp's n8 block; A row pitch ap, W row pitch NC (swizzled)
+template <int NC>
+__device__ __forceinline__ void mma_rows(float (&acc_m)[4], float (&acc_c)[4], const float* __restrict__ A, int ap,
+                                         const float* __restrict__ W, int nk8, int g, int t, int ncol) {
+#pragma unroll 4
+    for (int ks = 0; ks < nk8; ++ks) {
+        const int k0 = 8 * ks;
+        uint32_t ah[4], al[4], bh[2], bl[2];
+        split3(A[g * ap + k0 + t], ah[0], al[0]);
+        split3(A[(g + 8) * ap + k0 + t], ah[1], al[1]);
+        split3(A[g * ap + k0 + t + 4], ah[2], al[2]);
+        split3(A[(g + 8) * ap + k0 + t + 4], ah[3], al[3]);
+        const int col = ncol ^ (t << 3);
+        split3(W[(k0 + t) * NC + col], bh[0], bl[0]);
+        split3(W[(k0 + t + 4) * NC + col], bh[1], bl[1]);
+        mma_tf32(acc_c, al, bh[0], bh[1]);
+        mma_tf32(acc_c, ah, bl[0], bl[1]);
+        mma_tf32(acc_m, ah, bh[0], bh[1]);
+    }
+}
+}  // namespace
+
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NM_THREADS, 1) head_mma_kernel(HeadArgs a, int64_t wstream) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int q = (int)cluster.block_rank();
+    extern __shared__ __align__(16) float smem[];
+    float* wla = smem;                               // [384][96]
+    float* w1 = wla + HM_WLA;                        // [96][64]
+    float* w2 = w1 + HM_W1;                          // [64][32]
+    float* w3 = w2 + HM_W2;                          // [32][32]  (columns >= 21 are zero)
+    float* x = w3 + HM_W3;                           // [16][HM_XP]
+    float* y = x + NM_T * HM_XP;                     // [16][HM_YP]   relu(y) columns [96q, 96q+96)
+    float* xr = y + NM_T * HM_YP;                    // [16][64]      this CTA's partial of z1, read by the other three
+    float* z1 = xr + NM_T * 64;                      // [16][HM_Z1P]
+    float* z2 = z1 + NM_T * HM_Z1P;                  // [16][HM_Z2P]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int node0 = (blockIdx.x >> 2) * NM_T;
+    const float* wb = a.weights;
+
+    pdl_trigger();
+    {   // the CTA's whole weight block: 11520 16-byte granules, linear copy (already swizzled in global memory)
+        const float* src = wb + wstream + (size_t)q * HM_WFLOATS;
+        for (int i = threadIdx.x; i < HM_WFLOATS / 4; i += NM_THREADS) cp_async16(smem + i * 4, src + i * 4);
+        cp_async_commit();
+    }
+    // constants of this lane, fetched before the dependency wait
+    const int c0 = 8 * warp + 2 * t;                 // this lane's output columns c0, c0 + 1 inside a phase's n8 block
+    const float2 c_la = warp < 12 ? __ldg(reinterpret_cast<const float2*>(wb + a.la_b + 96 * q + c0)) : make_float2(0.f, 0.f);
+    const float c_sc = __ldg(wb + a.ddg), c_sh = __ldg(wb + a.ddg + 1);
+    const float2 c_m2 = warp < 4 ? __ldg(reinterpret_cast<const float2*>(wb + a.m2_b + c0)) : make_float2(0.f, 0.f);
+    float2 c_m3 = make_float2(0.f, 0.f);
+    if (warp < 3) { c_m3.x = c0 < 21 ? __ldg(wb + a.m3_b + c0) : 0.f; c_m3.y = c0 + 1 < 21 ? __ldg(wb + a.m3_b + c0 + 1) : 0.f; }
+    const float c_m1a = __ldg(wb + a.m1_b + (threadIdx.x & 63));                    // z1 reduction: thread <-> column tid % 64
+    pdl_wait();
+    // ---- x tile: [dec_last | dec_prev | W_s[S]] of the 16 residues
+    for (int i = threadIdx.x; i < NM_T * 96; i += NM_THREADS) {
+        const int r = i / 96, c4 = (i % 96) * 4, node = node0 + r;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (node < a.N) {
+            const int blk = c4 >> 7, cc = c4 & 127;
+            const float* src = blk == 0 ? a.dec_last + (size_t)node * HID : blk == 1 ? a.dec_prev + (size_t)node * HID
+                                        : wb + a.Ws + (size_t)a.S[node] * HID;
+            v = *reinterpret_cast<const float4*>(src + cc);
+        }
+        *reinterpret_cast<float4*>(x + r * HM_XP + c4) = v;
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    float am[4], ac[4];
+    // ---- LightAttention centre tap: columns [96q, 96q+96), 12 n8 blocks on warps 0..11, K = 384
+    if (warp < 12) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) am[i] = ac[i] = 0.f;
+        mma_rows<96>(am, ac, x, HM_XP, wla, 48, g, t, 8 * warp + g);
+        // both_out starts with a ReLU (transfer_model.py:67-71)
+        *reinterpret_cast<float2*>(y + g * HM_YP + c0) = make_float2(fmaxf(am[0] + ac[0] + c_la.x, 0.f), fmaxf(am[1] + ac[1] + c_la.y, 0.f));
+        *reinterpret_cast<float2*>(y + (g + 8) * HM_YP + c0) = make_float2(fmaxf(am[2] + ac[2] + c_la.x, 0.f), fmaxf(am[3] + ac[3] + c_la.y, 0.f));
+    }
+    __syncthreads();
+    // ---- both_out.1 (384 -> 64): this CTA's K slice = its 96 columns of relu(y); 8 n8 blocks on warps 0..7
+    if (warp < 8) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) am[i] = ac[i] = 0.f;
+        mma_rows<64>(am, ac, y, HM_YP, w1, 12, g, t, 8 * warp + g);
+        *reinterpret_cast<float2*>(xr + g * 64 + c0) = make_float2(am[0] + ac[0], am[1] + ac[1]);
+        *reinterpret_cast<float2*>(xr + (g + 8) * 64 + c0) = make_float2(am[2] + ac[2], am[3] + ac[3]);
+    }
+    cluster.sync();
+    {   // z1 = relu(sum of the four partials, in rank order, + b1): 1024 values, two per thread
+        const float* r0 = cluster.map_shared_rank(xr, 0);
+        const float* r1 = cluster.map_shared_rank(xr, 1);
+        const float* r2 = cluster.map_shared_rank(xr, 2);
+        const float* r3 = cluster.map_shared_rank(xr, 3);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int i = threadIdx.x + j * NM_THREADS, r = i >> 6, c = i & 63;
+            z1[r * HM_Z1P + c] = fmaxf(((r0[i] + r1[i]) + (r2[i] + r3[i])) + c_m1a, 0.f);
+        }
+    }
+    __syncthreads();
+    // ---- both_out.3 (64 -> 32) and both_out.5 (32 -> 21): every CTA computes them; 4 resp. 3 n8 blocks
+    if (warp < 4) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) am[i] = ac[i] = 0.f;
+        mma_rows<32>(am, ac, z1, HM_Z1P, w2, 8, g, t, 8 * warp + g);
+        *reinterpret_cast<float2*>(z2 + g * HM_Z2P + c0) = make_float2(fmaxf(am[0] + ac[0] + c_m2.x, 0.f), fmaxf(am[1] + ac[1] + c_m2.y, 0.f));
+        *reinterpret_cast<float2*>(z2 + (g + 8) * HM_Z2P + c0) = make_float2(fmaxf(am[2] + ac[2] + c_m2.x, 0.f), fmaxf(am[3] + ac[3] + c_m2.y, 0.f));
+    }
+    __syncthreads();
+    if (warp < 3 && q == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) am[i] = ac[i] = 0.f;
+        mma_rows<32>(am, ac, z2, HM_Z2P, w3, 4, g, t, 8 * warp + g);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int node = node0 + g + 8 * half;
+            if (node < a.N) {                        // ddg_out: Linear(1, 1) on each logit (transfer_model.py:110-111)
+                if (c0 < 21) a.table[(size_t)node * 21 + c0] = fmaf(am[2 * half] + ac[2 * half] + c_m3.x, c_sc, c_sh);
+                if (c0 + 1 < 21) a.table[(size_t)node * 21 + c0 + 1] = fmaf(am[2 * half + 1] + ac[2 * half + 1] + c_m3.y, c_sc, c_sh);
+            }
+        }
+    }
+    cluster.sync();      // no CTA may exit while another can still read its shared memory
+}
+
+static size_t smem_head_mma() {
+    return sizeof(float) * (HM_WFLOATS + NM_T * HM_XP + NM_T * HM_YP + NM_T * 64 + NM_T * HM_Z1P + NM_T * HM_Z2P);
+}
+
 static size_t smem_node_mma() {
     return sizeof(float) * (NM_SLOTS * WCHUNK_FLOATS + 2 * NM_T * NM_P + 2 * NM_T * HID + 2 * 2 * 16 * NM_T + NM_T);
 }
 
 cudaError_t node_mma_kernels_init() {
-    return cudaFuncSetAttribute(node_update_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_node_mma());
+    cudaError_t e = cudaFuncSetAttribute(node_update_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_node_mma());
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(head_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_head_mma());
+}
+
+void launch_head_mma(const HeadArgs& a, int64_t wstream, cudaStream_t st) {
+    launch_pdl(head_mma_kernel, dim3(4 * ((a.N + NM_T - 1) / NM_T)), dim3(NM_THREADS), smem_head_mma(), st, a, wstream);
 }
 
 void launch_node_update_mma(const NodeUpdArgs& a, cudaStream_t st) {

@@ -155,7 +155,7 @@ struct DevLayout {
     int64_t Ws;             // [21][128] embedding rows
     int64_t Wout, bout;     // ProteinMPNN W_out [21][128] row-major and its bias (log_probs)
     // default-cfg head (specialised kernels):
-    int64_t head;           // KN chunks: LA column blocks 0..2 (12 each) | both_out.1 (12) | .3 (2) | .5 (1), padded to 128 cols
+    int64_t head_mma;       // small-batch head: per cluster rank the LA / both_out slices it keeps in shared memory (4 x 46080 floats)
     int64_t tc_head;        // the same matrices as tensor-core images for the tcgen05 head (51 chunks)
     int64_t la_b, m1_b, m2_b, m3_b;
     int64_t ddg;            // [2] = scale, shift

@@ -15,7 +15,7 @@ timeout 300 python bench.py --workload c4 --steps 30 --no-cpu > $out/${tag}_benc
 timeout 300 python bench.py --workload c5 --steps 10 --no-cpu > $out/${tag}_bench_c5.json 2> $out/${tag}_bench_c5.err
 timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > $out/${tag}_bench_ref.json 2> $out/${tag}_bench_ref.err
 export TMPNN_GRAPHS=0      # under the profiler: direct launches (one kernel node = one launch either way)
-K='tc_edge_kernel|tc_edge_feat|tc_node_update|tc_head|node_update_mma|head_kernel|head_cluster|knn_kernel'
+K='tc_edge_kernel|tc_edge_feat|tc_node_update|tc_head|node_update_mma|head_mma|knn_kernel'
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches_c2.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-extra > $out/${tag}_ncu_c2.log 2>&1
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches_c3.csv python bench.py --workload c3 --steps 2 --warmup 3 --no-cpu > $out/${tag}_ncu_c3.log 2>&1
 for w in c3 c2 c5; do

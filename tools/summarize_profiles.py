@@ -11,7 +11,7 @@ G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 
 KNAMES = {"tc_edge_kernel<0": "tc_edge_upd", "tc_edge_kernel<1": "tc_enc_msg", "tc_edge_kernel<2": "tc_dec_msg",
           "tc_edge_feat_kernel": "tc_edge_feat", "tc_node_update_kernel": "tc_node_update", "node_update_mma_kernel": "node_update",
-          "tc_head_kernel": "tc_head", "head_kernel": "head", "head_cluster_kernel": "head", "knn_kernel": "knn"}
+          "tc_head_kernel": "tc_head", "head_mma_kernel": "head", "knn_kernel": "knn"}
 
 
 def short(name):
@@ -111,7 +111,7 @@ def full_capture(workload, cmd, traffic):
 
 
 if __name__ == "__main__":
-    K = "tc_edge_kernel|tc_edge_feat|tc_node_update|node_update_mma|head_kernel|head_cluster|knn_kernel"
+    K = "tc_edge_kernel|tc_edge_feat|tc_node_update|node_update_mma|head_mma|tc_head|knn_kernel"
     launch_list("c2", f"TMPNN_GRAPHS=0 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/{tag}_launches_c2.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-extra")
     launch_list("c3", f"TMPNN_GRAPHS=0 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/{tag}_launches_c3.csv python bench.py --workload c3 --steps 2 --warmup 3 --no-cpu")
     traffic = {"note": "dram__bytes_read.sum + dram__bytes_write.sum per launch (bytes), first captured launch of each kernel, from the "
