@@ -142,3 +142,31 @@ def test_megascale_on_the_reference_csv():
     assert n == 28172
     shape = np.load(os.path.join(os.path.dirname(__file__), "golden", "megascale_shape.npz"))
     assert len(shape["names"]) == 298 and len(shape["protein"]) == 271231
+
+
+def test_run_ssm_frame(tmp_path):
+    """Dataset-wide site saturation (analysis/SSM.py:93-164): frame layout, row order, pick_best / include_cys filtering."""
+    from thermompnn_b200.ssm import run_ssm
+
+    class FakeSSM:
+        def ssm_tables(self, pdbs):
+            out = []
+            for p in pdbs:
+                L = len(p["seq"])
+                t = np.add.outer(np.arange(L, dtype=np.float32), -0.01 * np.arange(20, dtype=np.float32))
+                t[[i for i, a in enumerate(p["seq"]) if a == "-"]] = np.nan
+                out.append(t)
+            return out
+    cfg, seqs = _mega_fixture(tmp_path, False)
+    ds = MegaScaleDataset(cfg, "all")
+    df = run_ssm("M", FakeSSM(), "Megascale-x", ds, centrality=True, include_cys=True)
+    assert list(df.columns) == ["WT Seq", "Model", "Dataset", "ddG_pred", "position", "wildtype", "mutation", "neighbors", "best_AA", "pdb"]
+    assert len(df) == 20 * (12 + 9) and df["mutation"][:20].tolist() == list("ACDEFGHIKLMNPQRSTVWY")
+    assert df["position"][20] == 1 and df["wildtype"][0] == seqs["p1.pdb"][0] and df["WT Seq"][0] == seqs["p1.pdb"]
+    assert abs(df["ddG_pred"][25] - (1 - 0.05)) < 1e-6 and df["neighbors"].notna().all()
+    no_cys = run_ssm("M", FakeSSM(), "Megascale-x", ds)
+    assert len(no_cys) == 19 * 21 and (no_cys["mutation"] != "C").all()
+    best = run_ssm("M", FakeSSM(), "Megascale-x", ds, pick_best=True, include_cys=True)
+    assert len(best) == 21 and (best["best_AA"] == "Y").all()      # column 19 (Y) has the lowest value in every row of the fake table
+    best_nc = run_ssm("M", FakeSSM(), "Megascale-x", ds, pick_best=True, include_cys=False)
+    assert (best_nc["best_AA"] == "Y").all()
