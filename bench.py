@@ -435,7 +435,8 @@ def run_ours(args, rank, world, local_rank):
     pdbs, desc, n_listed = make_workload(args.workload, world)
     job = Job(model, pdbs, dev, st)
     n_mut_total = 20 * job.total_residues                 # synthetic proteins have no gaps: 20 substitutions per residue
-    sampler = ClockSampler(range(world)) if rank == 0 else None
+    period = float(os.environ.get("TMPNN_BENCH_SAMPLE_PERIOD", "0.02"))
+    sampler = ClockSampler(range(world), period) if (rank == 0 and period > 0) else None
     if sampler:
         sampler.start()
     dev_ms, e2e_ms, launches_per_step, graph_steps, (prof, prof_n), region = measure(job, args.steps)
