@@ -42,6 +42,7 @@ if weak and os.path.exists(os.path.join(ROOT, "profiles", f"{tag}_scale_n1.json"
             f"({' / '.join(f'{weak[n]['ms_per_step']:.3f}' for n in sorted(weak))} ms).")
     if c5_1:
         tab += " C5 strong scaling: " + " / ".join(f"{c5_1['ms_per_step'] / (n * strong[n]['ms_per_step']):.2f}" for n in sorted(strong)) + f" ({c5_1['ms_per_step']:.1f} ms on one GPU)."
+tab += " The N = 8 figure varies between 0.73 and 0.87 from run to run (13 measurements, `profiles/r02_scaling.md`): the latency of the 8-rank all-gather, not the compute."
 tab += "\n(Box-to-box spread of one build is about ±3 %, the per-step collective's latency varies more; large batches run under `sw_power_cap` at ≈ 1.75 GHz.)"
 p = os.path.join(ROOT, "DESIGN.md")
 s = open(p).read()
