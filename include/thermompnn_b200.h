@@ -69,6 +69,9 @@ extern "C" {
 #define TMPNN_IN_DEVICE    1u   /* X, S, residue_idx, chain_enc, mask are device pointers on the context's device */
 #define TMPNN_OUT_DEVICE   2u   /* out_table is a device pointer */
 #define TMPNN_NO_SYNC      4u   /* do not synchronise the stream before returning (device in/out only) */
+#define TMPNN_UNCONDITIONAL 8u  /* tmpnn_run_batch_ex: out_log_probs = ProteinMPNN.unconditional_probs (no sequence input to the
+                                   decoder, protein_mpnn_utils.py:1557-1587) instead of the sequence-conditioned log_probs;
+                                   out_table must be NULL */
 
 typedef struct tmpnn_ctx tmpnn_ctx;
 

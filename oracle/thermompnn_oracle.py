@@ -220,6 +220,24 @@ def mpnn_forward(w, X, S, mask, residue_idx, chain_enc, top_k=TOP_K, trace: Opti
     return hidden[::-1], h_S
 
 
+def unconditional_log_probs(w, X, mask, residue_idx, chain_enc, top_k=TOP_K):
+    """ProteinMPNN.unconditional_probs (protein_mpnn_utils.py:1557-1587): the encoder as in ``mpnn_forward``; every
+    decoder layer then sees the FIXED input mask_i * [h_E | 0 | h_V_enc[j]] (no sequence, the neighbours' ENCODER states,
+    the order mask all zero so mask_bw = 0 and mask_fw = mask_i); log_softmax(W_out h_V) of the last layer, [L,21]."""
+    E, E_idx = edge_features(w, X, mask, residue_idx, chain_enc, top_k)
+    h_E = _lin(w, "prot_mpnn.W_e", E)
+    h_V = torch.zeros((E.shape[0], E.shape[-1]), dtype=E.dtype)
+    mask_attend = mask[:, None] * mask[E_idx]
+    for l in range(3):
+        h_V, h_E = enc_layer(w, l, h_V, h_E, E_idx, mask, mask_attend)
+    h_EX = torch.cat([h_E, torch.zeros_like(h_E)], -1)                 # cat_neighbors_nodes(zeros, h_E)   (:1573)
+    h_EXV = torch.cat([h_EX, _gather_nodes(h_V, E_idx)], -1)           # ... + h_V_enc[j]                  (:1574)
+    h_EXV_fw = mask[:, None, None] * h_EXV                             # mask_fw = mask_1D * (1 - 0)       (:1576-1582)
+    for l in range(3):
+        h_V = dec_layer(w, l, h_V, h_EXV_fw, mask)                     # (:1583-1584)
+    return log_probs(w, h_V)
+
+
 # --------------------------------------------------------------------------
 # transfer head
 # --------------------------------------------------------------------------

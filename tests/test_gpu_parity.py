@@ -445,3 +445,29 @@ def test_edge_states_match_oracle_on_every_edge(gpu_model, oracle_weights):
                 assert err <= 2e-4, (pdb["name"], key, err)
         finally:
             eng.set_debug_stop(0)
+
+
+def test_unconditional_probs_match_reference(gpu_baseline):
+    """ProteinMPNN.unconditional_probs (protein_mpnn_utils.py:1557-1587): the decoder layers gather the neighbours' ENCODER
+    states and no sequence; one ragged call, small-batch forms, then the same proteins inside a large batch (tcgen05 forms)."""
+    import os
+    from conftest import GOLDEN
+    ref = np.load(os.path.join(GOLDEN, "extra_unconditional.npz"))
+    names = list(ref.files)
+    pdbs = [load_case(n)[1] for n in names]
+    for n, lp in zip(names, gpu_baseline.unconditional_probs(pdbs[:2])):
+        err = np.abs(lp - ref[n]).max()
+        print(f"unconditional {n}: {err:.2e}")
+        assert err <= TOL
+    big = pdbs + [synth(300, 77)]
+    for n, lp in zip(names, gpu_baseline.unconditional_probs(big)):
+        assert np.abs(lp - ref[n]).max() <= TOL, n
+    # the sequence must not matter
+    a, b = load_case("synth40")[1], dict(load_case("synth40")[1])
+    b["seq"] = b["seq_chain_A"] = "A" * 40
+    assert np.array_equal(gpu_baseline.unconditional_probs([a])[0], gpu_baseline.unconditional_probs([b])[0])
+    from thermompnn_b200 import engine
+    eng = gpu_baseline._get_engine()
+    p = featurize_batch([a])
+    with pytest.raises(engine.EngineError, match="log-probabilities only"):
+        eng.run(p.offsets, p.X, p.S, p.residue_idx, p.chain_enc, p.mask, flags=engine.UNCONDITIONAL)

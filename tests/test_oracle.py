@@ -128,3 +128,15 @@ def test_oracle_cfg_variants(oracle_weights):
 def synth_by_name(pn):
     from thermompnn_b200.synth import synth
     return {"synth90": synth(90, seed=90), "synth40": synth(40, seed=7)}[pn]
+
+
+def test_oracle_unconditional_probs(oracle_weights):
+    """ProteinMPNN.unconditional_probs (protein_mpnn_utils.py:1557-1587): fixtures from the live reference."""
+    ref = np.load(os.path.join(GOLDEN, "extra_unconditional.npz"))
+    for name in ref.files:
+        _, pdb = load_case(name)
+        X, S, mask, ridx, cenc = O.featurize(pdb)
+        with torch.no_grad():
+            got = O.unconditional_log_probs(oracle_weights, torch.from_numpy(X), torch.from_numpy(mask), torch.from_numpy(ridx),
+                                            torch.from_numpy(cenc)).numpy()
+        assert np.abs(got - ref[name]).max() <= 2e-5, name

@@ -312,6 +312,9 @@ DevLayout prepare_weights(Prep& P, const tmpnn_model_cfg& cfg) {
         d.b2 = P.vec(p + "W2.bias");
         // h_S[j] term: W1[:, 256:384] . W_s[S_j]  -> one row per letter
         const float* W1 = P.find(p + "W1.weight");
+        d.qw_kn = P.alloc(HID * HID);
+        for (int k = 0; k < HID; ++k)
+            for (int n = 0; n < HID; ++n) P.dev[d.qw_kn + (int64_t)k * HID + n] = W1[(int64_t)n * 4 * HID + 3 * HID + k];
         d.Tseq = P.alloc(21 * HID);
         for (int a = 0; a < 21; ++a)
             for (int n = 0; n < HID; ++n) {
@@ -494,6 +497,7 @@ struct RunIO {
     float* host_table; float* host_logp;   // host destinations of the D2H copies, or NULL
     size_t stage_bytes;
     int B, N, lmax;
+    bool uncond;                        // TMPNN_UNCONDITIONAL: ProteinMPNN.unconditional_probs
 };
 
 // Enqueue the kernel chain of a call and the D2H of its results on `st` (the staged inputs are already on their way).
@@ -548,7 +552,7 @@ int enqueue_pipeline(tmpnn_ctx* ctx, const RunIO& io, cudaStream_t st) {
             } else {
                 const DecW& nx = L.dec[0];
                 a.proj[2] = {nx.b1, -1, ctx->P.p};
-                a.proj[3] = {-1, nx.Tseq, ctx->Q.p};
+                a.proj[3] = {-1, io.uncond ? (int64_t)-1 : nx.Tseq, ctx->Q.p};   // (no sequence term for unconditional_probs)
             }
             a.nproj = 4;
             { LaunchScope ls(ctx, st, node_update_uses_tcgen05(N) ? "tc_node_update" : "node_update"); launch_node_update(a, ctx->sm_count, st); }
@@ -560,12 +564,22 @@ int enqueue_pipeline(tmpnn_ctx* ctx, const RunIO& io, cudaStream_t st) {
             stage_done(3 + l);
         }
     }
+    // unconditional_probs (protein_mpnn_utils.py:1557-1587): every decoder layer gathers the neighbours' ENCODER state, so the
+    // layers' neighbour projections are computed once, here (P2 / Q2 are free after the encoder): layer 0's is already in Q
+    const float* Qdec[3] = {ctx->Q.p, ctx->Q.p, ctx->Q.p};
+    if (!done && io.uncond) {
+        const int64_t wk[2] = {L.dec[1].qw_kn, L.dec[2].qw_kn};
+        float* const outs[2] = {ctx->P2.p, ctx->Q2.p};
+        LaunchScope ls(ctx, st, "proj");
+        launch_proj(W, ctx->hV.p, 2, wk, outs, N, st);
+        Qdec[1] = ctx->P2.p; Qdec[2] = ctx->Q2.p;
+    }
     if (!done) {
         for (int l = 0; l < 3 && !done; ++l) {
             const DecW& d = L.dec[l];
             {
                 LaunchScope ls(ctx, st, "tc_dec_msg");
-                launch_tc_msg(true, ctx->hE.p, ctx->E_idx.p, ctx->P.p, HID, ctx->Q.p, HID, ctx->maskf.p, W + d.tc_msg, W + d.b2,
+                launch_tc_msg(true, ctx->hE.p, ctx->E_idx.p, ctx->P.p, HID, Qdec[l], HID, ctx->maskf.p, W + d.tc_msg, W + d.b2,
                               ctx->Spart.p, N, ctx->sm_count, st);
             }
             NodeUpdArgs a{};
@@ -578,7 +592,7 @@ int enqueue_pipeline(tmpnn_ctx* ctx, const RunIO& io, cudaStream_t st) {
                 const DecW& nx = L.dec[l + 1];
                 a.proj[0] = {nx.b1, -1, ctx->P.p};
                 a.proj[1] = {-1, nx.Tseq, ctx->Q.p};
-                a.nproj = 2;
+                a.nproj = io.uncond ? 1 : 2;            // unconditional: the neighbour projections are fixed (above)
             }
             { LaunchScope ls(ctx, st, node_update_uses_tcgen05(N) ? "tc_node_update" : "node_update"); launch_node_update(a, ctx->sm_count, st); }
             stage_done(6 + l);
@@ -789,6 +803,8 @@ int tmpnn_run_batch_ex(tmpnn_ctx* ctx, int32_t B, const int32_t* offsets, const 
     if (B <= 0 || !offsets || !X || !S || !residue_idx || !chain_enc || !mask)
         return fail(ctx, TMPNN_E_INVALID, "tmpnn_run_batch: NULL pointer or B <= 0");
     if (!out_table && !out_log_probs) return fail(ctx, TMPNN_E_INVALID, "tmpnn_run_batch: no output requested");
+    if ((flags & TMPNN_UNCONDITIONAL) && (out_table || !out_log_probs))
+        return fail(ctx, TMPNN_E_INVALID, "tmpnn_run_batch: TMPNN_UNCONDITIONAL produces log-probabilities only (out_table must be NULL)");
     if (out_table && !ctx->cfg.has_head)
         return fail(ctx, TMPNN_E_INVALID, "tmpnn_run_batch: the loaded model has no ddG head (has_head = 0); ask for log_probs only");
     if (offsets[0] != 0) return fail(ctx, TMPNN_E_INVALID, "tmpnn_run_batch: offsets[0] must be 0");
@@ -839,7 +855,7 @@ int tmpnn_run_batch_ex(tmpnn_ctx* ctx, int32_t B, const int32_t* offsets, const 
     }
     std::memcpy(ctx->h_stage + o_off, offsets, (size_t)(B + 1) * 4);
     RunIO io{};
-    io.B = B; io.N = N; io.lmax = lmax; io.stage_bytes = used;
+    io.B = B; io.N = N; io.lmax = lmax; io.stage_bytes = used; io.uncond = (flags & TMPNN_UNCONDITIONAL) != 0;
     io.off = reinterpret_cast<const int*>(ctx->d_in.p + o_off);
     io.X = X; io.S = S; io.r = residue_idx; io.c = chain_enc; io.m = mask;
     if (!in_dev) {

@@ -114,7 +114,42 @@ __global__ void __launch_bounds__(LP_THREADS) log_probs_kernel(LogProbArgs a) {
     }
 }
 
+// out_m[i][c] = sum_k h[i][k] W_m[k][c]: 16 residues per block, thread = output column (m = tid / 128), FP32.
+struct ProjArgs { const float* weights; const float* h; int nmat; int64_t w[3]; float* out[3]; int N; };
+constexpr int PJ_RT = 16;
+__global__ void __launch_bounds__(384) proj_kernel(ProjArgs a) {
+    __shared__ float hs[PJ_RT][HID];
+    pdl_trigger();
+    pdl_wait();
+    const int node0 = blockIdx.x * PJ_RT, m = threadIdx.x >> 7, c = threadIdx.x & 127;
+    for (int i = threadIdx.x; i < PJ_RT * HID; i += 384) {
+        const int node = node0 + i / HID;
+        hs[i / HID][i % HID] = node < a.N ? a.h[(size_t)node * HID + i % HID] : 0.f;
+    }
+    __syncthreads();
+    if (m >= a.nmat) return;
+    const float* W = a.weights + a.w[m];
+    float acc[PJ_RT];
+#pragma unroll
+    for (int t = 0; t < PJ_RT; ++t) acc[t] = 0.f;
+    for (int k = 0; k < HID; ++k) {
+        const float wv = __ldg(W + (size_t)k * HID + c);
+#pragma unroll
+        for (int t = 0; t < PJ_RT; ++t) acc[t] = fmaf(hs[t][k], wv, acc[t]);
+    }
+#pragma unroll
+    for (int t = 0; t < PJ_RT; ++t)
+        if (node0 + t < a.N) a.out[m][(size_t)(node0 + t) * HID + c] = acc[t];
+}
+
 cudaError_t head_kernels_init() { return cudaSuccess; }   // static shared memory only
+
+void launch_proj(const float* weights, const float* h, int nmat, const int64_t* w_kn, float* const* out, int N, cudaStream_t st) {
+    ProjArgs a{};
+    a.weights = weights; a.h = h; a.nmat = nmat; a.N = N;
+    for (int m = 0; m < nmat; ++m) { a.w[m] = w_kn[m]; a.out[m] = out[m]; }
+    launch_pdl(proj_kernel, dim3((N + PJ_RT - 1) / PJ_RT), dim3(384), 0, st, a);
+}
 
 void launch_head_generic(const HeadGenArgs& a, cudaStream_t st) {
     launch_pdl(head_generic_kernel, dim3((a.N + HG_RT - 1) / HG_RT), dim3(HG_THREADS), 0, st, a);

@@ -1,4 +1,6 @@
-// Host-visible launch interface of the kernel files (knn_kernel.cu, tc_edge_kernels.cu, node_kernels.cu, head_kernels.cu).
+// Host-visible launch interface of the kernel files: knn_kernel.cu, tc_edge_kernels.cu (edge features, messages, edge update),
+// node_mma_kernels.cu / tc_node_kernels.cu / tc_head_kernels.cu (per-residue kernels, small / large batches; node_kernels.cu
+// picks the form), head_kernels.cu (generic head, log_probs).
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -18,7 +20,7 @@ struct NodeUpdArgs {
     NodeUpdW w;
     const float* Spart;  // [N][3][128] per-16-row-block partial sums (tensor-core message kernel)
     const float* cnt_pre; // [N] sum of the edge weights per residue, computed once per call by the knn kernel
-    int64_t tc_img;      // tcgen05 form: weight images in the order that kernel consumes them (engine.cu: node_upd_tc)
+    int64_t tc_img;      // tcgen05 form: weight images in the order that kernel consumes them (engine.cu: Prep::node_upd)
     float* hV;           // [N][128] in/out
     float* hV_copy;      // optional second destination (decoder states kept for the head)
     const float* maskf;  // [N]
@@ -26,7 +28,7 @@ struct NodeUpdArgs {
     ProjSpec proj[4];
     int nproj;
     int N;
-    long long* trace;    // optional (TMPNN_TC_TRACE=1, dev tool): clock64() phase stamps of cluster 0, CTA 0
+    long long* trace;    // optional (-DTMPNN_DEV build + TMPNN_TC_TRACE=1): clock64() phase stamps of block 0
 };
 
 struct HeadArgs {
@@ -80,6 +82,9 @@ void launch_knn(const int* offsets, int B, const float* X, const uint8_t* mask, 
                 float* maskf, int* S_out, int* err_flag, int* E_idx, float* D_nb, float* cnt_enc, float* cnt_dec, cudaStream_t st);
 void launch_head_generic(const HeadGenArgs& a, cudaStream_t st);
 void launch_log_probs(const LogProbArgs& a, cudaStream_t st);
+// out_m[i] = h[i] . W_m for up to three [128 k][128 n] matrices (unconditional_probs: the decoder layers' neighbour projections
+// of the ENCODER state, computed once)
+void launch_proj(const float* weights, const float* h, int nmat, const int64_t* w_kn, float* const* out, int N, cudaStream_t st);
 void launch_tc_edge_upd(float* hE, const int* E_idx, const float* P, const float* Q, const float* maskf, const float* wimg,
                         const float* b12, const float* b13, const float* ln_g, const float* ln_b, int N, int sms, cudaStream_t st,
                         long long* trace = nullptr);

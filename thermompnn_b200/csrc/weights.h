@@ -141,6 +141,7 @@ struct DecW {
     int64_t tc_msg;         // [W1b | W2] images  (W1b = h_E block of the 512-wide W1)
     int64_t b1, b2;
     int64_t Tseq;           // [21][128] = W_s . W1c^T : the h_S[j] term folded per letter
+    int64_t qw_kn;          // W1[:, 384:512] as [128 k][128 n] fp32: the h_V[j] projection on its own (unconditional_probs)
     NodeUpdW nu;
 };
 

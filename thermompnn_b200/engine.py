@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libthermompnn_b200_dev.so" if os.environ.get("TMPNN_LIB") == "dev" else "libthermompnn_b200.so")
 MAX_HIDDEN = 8
 
-IN_DEVICE, OUT_DEVICE, NO_SYNC = 1, 2, 4
+IN_DEVICE, OUT_DEVICE, NO_SYNC, UNCONDITIONAL = 1, 2, 4, 8
 
 # every symbol include/thermompnn_b200.h declares
 SYMBOLS = [

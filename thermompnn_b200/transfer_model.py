@@ -223,6 +223,14 @@ class ProteinMPNNBaseline(_EngineModule):
                                        want_table=False, log_probs=True)
         return [lp[packed.offsets[b]:packed.offsets[b + 1]] for b in range(packed.n_proteins)]
 
+    def unconditional_probs(self, pdbs: Sequence[dict]) -> List[np.ndarray]:
+        """``ProteinMPNN.unconditional_probs`` (protein_mpnn_utils.py:1557-1587) for each protein: [L_b, 21] log-probabilities
+        from the structure alone -- the decoder sees no sequence and the neighbours' encoder states."""
+        packed = featurize_batch(pdbs)
+        _, lp = self._get_engine().run(packed.offsets, packed.X, packed.S, packed.residue_idx, packed.chain_enc, packed.mask,
+                                       want_table=False, log_probs=True, flags=_engine.UNCONDITIONAL)
+        return [lp[packed.offsets[b]:packed.offsets[b + 1]] for b in range(packed.n_proteins)]
+
     def forward(self, pdb, mutations, tied_feat=True):
         lp = self.log_prob_tables([pdb[0]])[0]
         log_probs = torch.from_numpy(lp).to(self.weight_blob.device)        # one H2D; per-mutation results are views
