@@ -220,3 +220,29 @@ def test_engine_run_validates_host_buffers():
         e.run(*args, want_table=False)
     with pytest.raises(ValueError, match="sizes do not match"):
         e.run(p.offsets, p.X[:5], p.S, p.residue_idx, p.chain_enc, p.mask)
+
+
+def test_predict_batch_lookup_logic_on_a_fake_table(monkeypatch):
+    """forward / predict_batch around the device call: list alignment, None entries, wt subtraction, negative positions,
+    one tensor shared by all results (the device pass itself is replaced by a fake table; CPU only)."""
+    import torch
+    from thermompnn_b200.transfer_model import TransferModel, get_trained_model
+    m = get_trained_model(CKPT, override_custom=True)
+    pdbs = [synth(12, 1), synth(9, 2)]
+    tabs = [np.arange(12 * 21, dtype=np.float32).reshape(12, 21), -np.arange(9 * 21, dtype=np.float32).reshape(9, 21)]
+    monkeypatch.setattr(TransferModel, "head_tables", lambda self, p: tabs[:len(p)])
+    muts0 = [Mutation(0, pdbs[0]["seq"][0], "C"), None, Mutation(-1, pdbs[0]["seq"][-1], "Y")]
+    muts1 = [Mutation(4, pdbs[1]["seq"][4], "A")]
+    outs = m.predict_batch([([pdbs[0]], muts0), (pdbs[1], muts1)])
+    assert outs[0][1] is None and len(outs[0]) == 3 and len(outs[1]) == 1
+    A = ALPHABET.index
+    assert outs[0][0]["ddG"].item() == tabs[0][0, A("C")] - tabs[0][0, A(pdbs[0]["seq"][0])]
+    assert outs[0][2]["ddG"].item() == tabs[0][11, A("Y")] - tabs[0][11, A(pdbs[0]["seq"][-1])]
+    assert outs[1][0]["ddG"].item() == tabs[1][4, A("A")] - tabs[1][4, A(pdbs[1]["seq"][4])]
+    assert outs[0][0]["ddG"].shape == (1,) and outs[0][0]["ddG"].dtype == torch.float32
+    assert outs[0][0]["ddG"].untyped_storage().data_ptr() == outs[1][0]["ddG"].untyped_storage().data_ptr()
+    pred, extra = m([pdbs[0]], muts0)
+    assert extra is None and pred[1] is None and torch.equal(pred[0]["ddG"], outs[0][0]["ddG"])
+    assert m.predict_batch([]) == [] and m([pdbs[0]], [None])[0] == [None]
+    with pytest.raises(ValueError):
+        m([pdbs[0]], [Mutation(0, "A", "B")])

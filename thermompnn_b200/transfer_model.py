@@ -186,11 +186,12 @@ class TransferModel(_EngineModule):
         looked = [self._lookup(T, muts) for T, (_, muts) in zip(tables, batch)]
         flat = np.concatenate([v for _, v in looked]) if looked else np.zeros(0, np.float32)
         flat_t = torch.from_numpy(flat).to(self.weight_blob.device)
+        views = flat_t.split(1) if flat_t.numel() else ()     # shape-[1] views of ONE device tensor (one C++ call, not one slice per mutation)
         outs, o = [], 0
         for (idx, v), (_, muts) in zip(looked, batch):
             out: List[Optional[dict]] = [None] * len(muts)
             for k, i in enumerate(idx):
-                out[i] = {"ddG": flat_t[o + k:o + k + 1]}
+                out[i] = {"ddG": views[o + k]}
             o += len(idx)
             outs.append(out)
         return outs
