@@ -246,3 +246,21 @@ def test_predict_batch_lookup_logic_on_a_fake_table(monkeypatch):
     assert m.predict_batch([]) == [] and m([pdbs[0]], [None])[0] == [None]
     with pytest.raises(ValueError):
         m([pdbs[0]], [Mutation(0, "A", "B")])
+
+
+def test_array_coordinates_pack_identically():
+    """``arrays=True`` (numpy coordinates instead of upstream's nested lists) changes the container, not a single value."""
+    from thermompnn_b200.pdb import alt_parse_PDB
+    a, b = [synth(50, 3, gaps=[4, 9]), synth(33, 4)], [synth(50, 3, gaps=[4, 9], arrays=True), synth(33, 4, arrays=True)]
+    pa, pb = featurize_batch(a), featurize_batch(b)
+    for k in ("offsets", "X", "S", "residue_idx", "chain_enc", "mask"):
+        assert np.array_equal(getattr(pa, k), getattr(pb, k)), k
+    pdb_path = os.path.join(GOLDEN, "2OCJ.pdb")
+    x, y = alt_parse_PDB(pdb_path, "AB"), alt_parse_PDB(pdb_path, "AB", arrays=True)
+    assert isinstance(y[0]["coords_chain_B"]["CA_chain_B"], np.ndarray) and x[0]["seq"] == y[0]["seq"]
+    fx, fy = featurize_batch(x), featurize_batch(y)
+    assert np.array_equal(fx.X, fy.X) and np.array_equal(fx.mask, fy.mask)
+    with pytest.raises(ValueError, match="do not match sequence length"):
+        bad = synth(10, 1)
+        bad["coords_chain_A"]["CA_chain_A"] = bad["coords_chain_A"]["CA_chain_A"][:9]
+        featurize_batch([bad])

@@ -32,37 +32,54 @@ class Packed:
     def n_residues(self): return int(self.offsets[-1])
 
 
-def featurize_one(pdb: dict):
+def _chains(pdb: dict):
+    """Per chain of one protein, in dict order: (x [n,4,3] float64 with NaN for missing, letters [n] int32, n)."""
     letters = [k[-1:] for k in pdb if k[:10] == "seq_chain_"]   # dict order, as protein_mpnn_utils.py:387
     if not letters:
         raise ValueError("protein dict has no 'seq_chain_*' entries")
-    xs, ss, cs, rs = [], [], [], []
-    pos = 0
-    for c, ch in enumerate(letters, start=1):
+    out = []
+    for ch in letters:
         seq = pdb[f"seq_chain_{ch}"]
         co = pdb[f"coords_chain_{ch}"]
-        x = np.stack([np.asarray(co[f"{a}_chain_{ch}"], dtype=np.float64) for a in ("N", "CA", "C", "O")], 1)
         n = len(seq)
-        if x.shape != (n, 4, 3):
-            raise ValueError(f"chain {ch}: coordinates {x.shape} do not match sequence length {n}")
+        x = np.empty((n, 4, 3), dtype=np.float64)
+        for i, a in enumerate(("N", "CA", "C", "O")):           # nested lists (upstream's schema) or [n,3] arrays
+            v = np.asarray(co[f"{a}_chain_{ch}"], dtype=np.float64)
+            if v.shape != (n, 3):
+                raise ValueError(f"chain {ch}: coordinates {(v.shape[0], 4, 3) if v.ndim == 2 else v.shape} do not match sequence length {n}")
+            x[:, i, :] = v
         s = _LUT[np.frombuffer(seq.encode("ascii"), dtype=np.uint8)]
         if (s < 0).any():
             bad = seq[int(np.argmax(s < 0))]
             raise ValueError(f"'{bad}' is not in list")       # what ALPHABET.index raises upstream (:568)
-        xs.append(x); ss.append(s)
-        cs.append(np.full(n, c, dtype=np.int32))                       # 1-based chain label (:471)
-        rs.append((100 * (c - 1) + np.arange(pos, pos + n)).astype(np.int32))   # (:473)
-        pos += n
+        out.append((x, s, n))
+    return out
+
+
+def _pack(protein_chains):
+    """[[(x, s, n) per chain] per protein] -> Packed: label arrays per chain, NaN handling once on the whole batch."""
+    xs, ss, cs, rs, lens = [], [], [], [], []
+    for chains in protein_chains:
+        pos = 0
+        for c, (x, s, n) in enumerate(chains, start=1):
+            xs.append(x); ss.append(s)
+            cs.append(np.full(n, c, dtype=np.int32))                               # 1-based chain label (:471)
+            rs.append(np.arange(100 * (c - 1) + pos, 100 * (c - 1) + pos + n, dtype=np.int32))   # (:473)
+            pos += n
+        lens.append(pos)
     X = np.concatenate(xs, 0)
-    mask = np.isfinite(X.sum((1, 2)))                                   # (:576)
-    X = np.where(np.isnan(X), 0.0, X).astype(np.float32)               # (:577, :595)
-    return X, np.concatenate(ss), np.concatenate(rs), np.concatenate(cs), mask.astype(np.uint8)
+    mask = np.isfinite(X.reshape(X.shape[0], 12).sum(1))                           # (:576)
+    X = np.nan_to_num(X, nan=0.0, posinf=np.inf, neginf=-np.inf).astype(np.float32)   # NaN -> 0 (:577), cast (:595)
+    offsets = np.zeros(len(lens) + 1, dtype=np.int32)
+    offsets[1:] = np.cumsum(lens)
+    return Packed(offsets, np.ascontiguousarray(X), np.ascontiguousarray(np.concatenate(ss)), np.concatenate(rs), np.concatenate(cs),
+                  mask.astype(np.uint8))
+
+
+def featurize_one(pdb: dict):
+    p = _pack([_chains(pdb)])
+    return p.X, p.S, p.residue_idx, p.chain_enc, p.mask
 
 
 def featurize_batch(pdbs: Sequence[dict]) -> Packed:
-    parts = [featurize_one(p) for p in pdbs]
-    lens = np.asarray([p[0].shape[0] for p in parts], dtype=np.int64)
-    offsets = np.zeros(len(parts) + 1, dtype=np.int32)
-    offsets[1:] = np.cumsum(lens)
-    cat = lambda i: np.ascontiguousarray(np.concatenate([p[i] for p in parts], 0))
-    return Packed(offsets, cat(0), cat(1), cat(2), cat(3), cat(4))
+    return _pack([_chains(p) for p in pdbs])

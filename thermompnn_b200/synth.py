@@ -45,11 +45,12 @@ def synth_backbone(L: int, rng: np.random.Generator) -> np.ndarray:
 
 
 def synth(L: int, seed: int, seq: Optional[str] = None, name: Optional[str] = None,
-          chain: str = "A", gaps: Optional[List[int]] = None) -> dict:
+          chain: str = "A", gaps: Optional[List[int]] = None, arrays: bool = False) -> dict:
     """One synthetic single-chain protein as an ``alt_parse_PDB``-style dict.
 
     ``gaps`` lists positions to turn into missing residues ('-' in ``seq`` and
-    NaN coordinates), the way ``alt_parse_PDB`` reports unresolved residues.
+    NaN coordinates), the way ``alt_parse_PDB`` reports unresolved residues.  ``arrays=True`` keeps the coordinates as
+    numpy arrays instead of nested lists (same values; cheaper to pack).
     """
     rng = np.random.default_rng(seed)
     X = synth_backbone(L, rng)
@@ -68,10 +69,10 @@ def synth(L: int, seed: int, seq: Optional[str] = None, name: Optional[str] = No
         "seq": seq,
         f"seq_chain_{chain}": seq,
         f"coords_chain_{chain}": {
-            f"N_chain_{chain}": X[:, 0].tolist(),
-            f"CA_chain_{chain}": X[:, 1].tolist(),
-            f"C_chain_{chain}": X[:, 2].tolist(),
-            f"O_chain_{chain}": X[:, 3].tolist(),
+            f"N_chain_{chain}": np.ascontiguousarray(X[:, 0]) if arrays else X[:, 0].tolist(),
+            f"CA_chain_{chain}": np.ascontiguousarray(X[:, 1]) if arrays else X[:, 1].tolist(),
+            f"C_chain_{chain}": np.ascontiguousarray(X[:, 2]) if arrays else X[:, 2].tolist(),
+            f"O_chain_{chain}": np.ascontiguousarray(X[:, 3]) if arrays else X[:, 3].tolist(),
         },
     }
 

@@ -153,7 +153,12 @@ class TransferModel(_EngineModule):
     # ---- batched entries (new capability: the reference is strictly B = 1) ------------------
     def head_tables(self, pdbs: Sequence[dict]) -> List[np.ndarray]:
         """[L_b, 21] head outputs T for each protein (host numpy).  ddG(i, wt->a) = T[i,a] - T[i,wt]."""
-        packed = featurize_batch(pdbs)
+        return self.head_tables_packed(featurize_batch(pdbs))
+
+    def head_tables_packed(self, packed: Packed) -> List[np.ndarray]:
+        """The same from an already packed batch (``featurize.featurize_batch``): packing costs ~1.4 us per residue on the
+        host with upstream's nested-list coordinates (0.1 us with numpy arrays) -- more than the GPU pass on large batches --
+        so callers that scan one set of structures repeatedly pack once."""
         T = self._get_engine().run(packed.offsets, packed.X, packed.S, packed.residue_idx, packed.chain_enc, packed.mask)
         return [T[packed.offsets[b]:packed.offsets[b + 1]] for b in range(packed.n_proteins)]
 
